@@ -1,0 +1,152 @@
+/* yl11.h — C-ABI of libyl11.so: the B200 (sm_100a) kernels behind the YOLO11 inference path of YOLO-Lite.
+ *
+ * The reference (dongyunjinyu/YOLO-Lite) is pure Python and has no FFI; every entry point below replaces a
+ * *library call site* of the reference (ATen / cuDNN / torchvision), cited as `file:line` relative to the
+ * reference root.  The reference-side binding is a ctypes stub; the shipped binding is
+ * yolo-lite_b200/yololite/_C.py.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*), never allocates,
+ *     never synchronises, and is CUDA-graph capturable;
+ *   - return 0 on success, negative yl_status on failure; yl_last_error_string() gives the text
+ *     (thread-local);
+ *   - activations are NHWC ("pixel major") bf16; a yl_tensor is a channel slice [coff, coff+c) of a buffer
+ *     with `cstride` channels per pixel, so channel-concat is aliasing, not a copy.
+ */
+#ifndef YL11_H
+#define YL11_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YL11_VERSION 100
+
+typedef enum yl_status {
+    YL_OK = 0,
+    YL_ERR_ARG = -1,       /* bad shape / alignment / null pointer            */
+    YL_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed             */
+    YL_ERR_UNSUPPORTED = -3,
+    YL_ERR_WORKSPACE = -4, /* workspace too small                              */
+    YL_ERR_NO_DEVICE = -5  /* no sm_100 device: the library has no CPU path    */
+} yl_status;
+
+typedef enum yl_dtype { YL_BF16 = 0, YL_F32 = 1 } yl_dtype;
+typedef enum yl_act { YL_ACT_NONE = 0, YL_ACT_SILU = 1 } yl_act;
+typedef enum yl_conv_impl { YL_IMPL_AUTO = 0, YL_IMPL_DIRECT = 1, YL_IMPL_TCGEN05 = 2 } yl_conv_impl;
+
+/* NHWC view: element (n,h,w,ch) lives at data[((n*h_dim + h)*w_dim + w)*cstride + coff + ch]. */
+typedef struct yl_tensor {
+    void* data;
+    int32_t n, h, w, c;
+    int32_t cstride; /* channels per pixel of the underlying buffer (>= coff + c) */
+    int32_t coff;    /* first channel of the slice                               */
+    int32_t dtype;   /* yl_dtype                                                  */
+    int32_t _pad;
+} yl_tensor;
+
+/* ---- runtime ------------------------------------------------------------------------------------------- */
+int yl_version(void);
+const char* yl_last_error_string(void);
+/* Bind to `device`, check it is sm_100, resolve the TMA encoder and opt kernels into large shared memory.
+ * Must be called once per process before any other entry point. */
+int yl_init(int device);
+
+/* ---- weight preparation (one-time) ----------------------------------------------------------------------
+ * Replaces the fold the reference never performs at inference (utils/torch_utils.py:182-209 is the formula:
+ * w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps) [+ conv bias scaled]).
+ * Dense: w_oihw [co][ci][k][k] fp32 -> packed bf16 [co_pad][k*k][ci_pad] (tap-major, channel-minor = the
+ * K order of the implicit GEMM).  Depthwise (ci == 1, depthwise != 0): -> bf16 [k*k][co_pad].
+ * gamma/beta/mean/var may all be NULL (plain nn.Conv2d, head.py:39,48); conv_bias may be NULL. */
+int yl_fold_bn_pack(const float* w_oihw, const float* gamma, const float* beta, const float* mean,
+                    const float* var, const float* conv_bias, float eps, int co, int ci, int k, int co_pad,
+                    int ci_pad, int depthwise, void* w_packed, float* bias_out, void* stream);
+
+/* ---- layout ------------------------------------------------------------------------------------------- */
+/* predictor.py:81-84 (`.to(device).float()`): NCHW fp32 image batch -> NHWC bf16 slice. */
+int yl_nchw_to_nhwc(const float* x_nchw, const yl_tensor* y, void* stream);
+/* NHWC slice (bf16 or f32) -> dense NCHW fp32 (module-level API returns reference-layout tensors). */
+int yl_nhwc_to_nchw(const yl_tensor* x, float* y_nchw, void* stream);
+/* conv.py:321-331 Concat fallback when aliasing is impossible: copy a channel slice into another. */
+int yl_copy_slice(const yl_tensor* x, const yl_tensor* y, void* stream);
+/* nn.Upsample(None, 2, "nearest") (cfg/yolo11.yaml:31,35): y is (n, 2h, 2w, c). */
+int yl_upsample2x(const yl_tensor* x, const yl_tensor* y, void* stream);
+
+/* ---- convolution ---------------------------------------------------------------------------------------
+ * Replaces Conv.forward = act(bn(conv(x))) (nn/modules/conv.py:35-53), Bottleneck's residual add
+ * (block.py:343), the PSABlock adds (block.py:951-952) and the torch.cat that follows a conv
+ * (block.py:233-235, 259, 184) via the output slice.  Dense k in {1,3}, stride in {1,2}, pad = k/2.
+ *   y = [res +] act(conv(x, w) + bias)
+ * `y.h/y.w` are the conv output dims; with upsample2x != 0 each result pixel is replicated into the 2x2
+ * block of a (n, 2h, 2w) buffer described by `y` (then y.h/y.w are the *upsampled* dims). */
+typedef struct yl_conv_args {
+    yl_tensor x;
+    yl_tensor y;   /* bf16 or f32 */
+    yl_tensor res; /* res.data == NULL: no residual; else same dims as the conv output, bf16 */
+    const void* w; /* packed by yl_fold_bn_pack                                              */
+    const float* bias;
+    int32_t k, stride;
+    int32_t ci_pad, co_pad; /* packed weight dims; x.c <= ci_pad, y.c <= co_pad             */
+    int32_t act;            /* yl_act                                                         */
+    int32_t upsample2x;
+    int32_t impl;           /* yl_conv_impl                                                   */
+    int32_t _pad;
+} yl_conv_args;
+int yl_conv_bn_act(const yl_conv_args* a, void* stream);
+/* 1 if the tcgen05 implicit-GEMM path can run this problem, 0 if it needs the direct kernel. */
+int yl_conv_tc_supported(const yl_conv_args* a);
+
+/* DWConv (conv.py:100-105), depthwise 3x3 stride 1 pad 1 + folded BN (+SiLU): head.py:46-47, block.py:893.
+ * w is bf16 [9][c]; optional residual-style `add` tensor is summed after activation (Attention: + pe(v)). */
+int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const float* bias, int act,
+                 const yl_tensor* add, void* stream);
+
+/* SPPF's three chained MaxPool2d(5,1,2) (block.py:182-184), -inf padding; y1=m(x), y2=m(y1), y3=m(y2). */
+int yl_sppf_pool(const yl_tensor* x, const yl_tensor* y1, const yl_tensor* y2, const yl_tensor* y3, int k,
+                 void* stream);
+
+/* Attention core (block.py:905-914): qkv is (n,h,w,heads*(2*kd+hd)) with per-head channel groups [q|k|v];
+ * out[(n,i), head*hd + c] = sum_j softmax_j(scale * q_i.k_j) v_j[c].  `+ pe(v)` and `proj` are separate calls. */
+int yl_psa_attention(const yl_tensor* qkv, const yl_tensor* out, int heads, int key_dim, int head_dim,
+                     float scale, void* stream);
+
+/* ---- Detect decode --------------------------------------------------------------------------------------
+ * Replaces Detect._inference + DFL + make_anchors + dist2bbox (head.py:95-126, block.py:51-69,
+ * tal.py:326-350).  levels[i] is the raw head map of level i, NHWC f32 with 4*reg_max + nc channels
+ * (box bins first).  y is dense fp32 (B, 4+nc, A), A = sum h_i*w_i, anchors ordered level-major,
+ * row-major inside a level: y[:, :4] = (cx, cy, w, h) * stride, y[:, 4:] = sigmoid(cls). */
+int yl_detect_decode(const yl_tensor* levels, int nl, const float* strides_host, int reg_max, int nc, float* y,
+                     void* stream);
+
+/* ---- NMS ------------------------------------------------------------------------------------------------
+ * Replaces ops.non_max_suppression (utils/ops.py:138-273) including torchvision.ops.nms (ops.py:265):
+ * candidate filter (strict >), best-class or multi-label expansion, optional class filter, max_nms top-k,
+ * fp32 class offset `cls * max_wh`, stable descending sort, greedy IoU suppression with torchvision's CPU
+ * arithmetic, first max_det survivors.  pred is dense fp32 (B, 4+nc, A), boxes as (cx, cy, w, h).
+ * out: (B, max_det, 6) fp32 rows [x1,y1,x2,y2,conf,cls] in descending score order; counts: (B) int32.
+ * classes_dev: optional int32[n_classes] device array (NULL = all classes). */
+size_t yl_nms_workspace_bytes(int B, int A, int nc, int multi_label);
+int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, double iou_thres,
+                   const int32_t* classes_dev, int n_classes, int agnostic, int multi_label, int max_det,
+                   int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out,
+                   int32_t* counts, void* stream);
+/* torchvision.ops.nms semantics on explicit boxes (n,4) xyxy + scores (n): keep (int64[n]) gets the kept
+ * indices in descending score order, *count their number.  workspace >= yl_nms_boxes_workspace_bytes(n). */
+size_t yl_nms_boxes_workspace_bytes(int n);
+int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thres, void* workspace,
+                 size_t workspace_bytes, int64_t* keep, int32_t* count, void* stream);
+/* ops.py:213 in_place=True side effect: pred[:, :4] (cx,cy,w,h) -> (x1,y1,x2,y2), xywh2xyxy ops.py:372-389. */
+int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream);
+/* ops.scale_boxes + clip_boxes (utils/ops.py:66-98, 276-295) on the padded (B,max_det,6) detections:
+ * per image: box -= (padx,pady); box /= gain; clamp to (0..w0, 0..h0).  params_dev: float[B][5] =
+ * {gain, padx, pady, w0, h0}. */
+int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YL11_H */

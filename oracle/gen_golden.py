@@ -1,0 +1,189 @@
+"""oracle/gen_golden.py — regenerate tests/golden/*.npz from the reference itself (build container only).
+
+    python oracle/gen_golden.py
+
+Fixtures (all seeded; weights are the name-keyed values of oracle/weights.py, so they are not stored):
+  model_yolo11{n,s,m}.npz   reference DetectionModel forward on a (2,3,64,64) batch: y, raw head maps
+  modules.npz               reference nn modules (Conv, DWConv, Bottleneck, C3k, C3k2 x2, SPPF, Attention,
+                            PSABlock, C2PSA, Detect, DFL) on small inputs
+  nms_torchvision.npz       torchvision.ops.nms (CPU, the arithmetic behind ops.py:265) known-answer cases
+  nms_reference.npz         reference ops.non_max_suppression (max_time_img=1e9) on synthetic predictions
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle.ref_harness import build_reference_model, import_reference  # noqa: E402
+from oracle.weights import fill_state_dict_  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+
+def seeded(shape, seed, lo=0.0, hi=1.0):
+    g = np.random.default_rng(seed)
+    return torch.from_numpy(g.uniform(lo, hi, shape).astype(np.float32))
+
+
+def gen_models():
+    for scale in "nsm":
+        m = build_reference_model(scale)
+        fill_state_dict_(m)
+        x = seeded((2, 3, 64, 64), 100)
+        with torch.no_grad():
+            y, raw = m(x)
+        shapes = {k: np.asarray(v.shape, dtype=np.int64) for k, v in m.state_dict().items()}
+        np.savez_compressed(GOLD / f"model_yolo11{scale}.npz", x=x.numpy(), y=y.numpy(),
+                            **{f"raw{i}": r.numpy() for i, r in enumerate(raw)},
+                            keys=np.array(list(shapes)), shapes=np.array([list(s) + [0] * (4 - len(s)) for s in shapes.values()]),
+                            ndims=np.array([len(s) for s in shapes.values()]))
+        print("model", scale, tuple(y.shape), float(y[:, 4:].max()))
+
+
+def gen_modules():
+    import_reference()
+    from yololite.nn.modules.block import C2PSA, C3k, C3k2, DFL, SPPF, Attention, Bottleneck, PSABlock
+    from yololite.nn.modules.conv import Conv, DWConv
+    from yololite.nn.modules.head import Detect
+
+    out = {}
+
+    def run(tag, mod, x):
+        fill_state_dict_(mod.eval())
+        with torch.no_grad():
+            y = mod(x)
+        out[f"{tag}.x"] = x.numpy()
+        out[f"{tag}.y"] = y.numpy()
+        print("module", tag, tuple(x.shape), "->", tuple(y.shape))
+
+    run("conv_k3s2", Conv(16, 32, 3, 2), seeded((2, 16, 20, 24), 1, -1, 1))
+    run("conv_k1", Conv(48, 64, 1, 1), seeded((2, 48, 12, 12), 2, -1, 1))
+    run("conv_k3s1_noact", Conv(32, 16, 3, 1, act=False), seeded((1, 32, 10, 14), 3, -1, 1))
+    run("conv_stem", Conv(3, 16, 3, 2), seeded((2, 3, 32, 32), 4, 0, 1))
+    run("dwconv", DWConv(64, 64, 3), seeded((2, 64, 10, 10), 5, -1, 1))
+    run("bottleneck", Bottleneck(32, 32, True), seeded((2, 32, 12, 12), 6, -1, 1))
+    run("c3k", C3k(64, 64, 2), seeded((1, 64, 10, 10), 7, -1, 1))
+    run("c3k2_plain", C3k2(64, 128, 1, False, 0.25), seeded((2, 64, 12, 12), 8, -1, 1))
+    run("c3k2_c3k", C3k2(128, 128, 1, True), seeded((1, 128, 8, 8), 9, -1, 1))
+    run("sppf", SPPF(128, 128, 5), seeded((2, 128, 9, 11), 10, -1, 1))
+    run("attention", Attention(128, num_heads=2, attn_ratio=0.5), seeded((2, 128, 6, 7), 11, -1, 1))
+    run("psablock", PSABlock(128, 0.5, 2), seeded((1, 128, 5, 5), 12, -1, 1))
+    run("c2psa", C2PSA(256, 256, 1), seeded((1, 256, 6, 6), 13, -1, 1))
+    # DFL: input (b, 64, a)
+    dfl = DFL(16).eval()
+    xd = seeded((2, 64, 50), 14, -3, 3)
+    with torch.no_grad():
+        out["dfl.x"], out["dfl.y"] = xd.numpy(), dfl(xd).numpy()
+    # Detect on three levels (8x8, 4x4, 2x2), strides set like DetectionModel does
+    det = Detect(80, (64, 128, 256)).eval()
+    det.stride = torch.tensor([8.0, 16.0, 32.0])
+    fill_state_dict_(det)
+    feats = [seeded((2, c, s, s), 20 + i, -1, 1) for i, (c, s) in enumerate(((64, 8), (128, 4), (256, 2)))]
+    with torch.no_grad():
+        y, raw = det([f.clone() for f in feats])
+    for i, f in enumerate(feats):
+        out[f"detect.x{i}"] = f.numpy()
+        out[f"detect.raw{i}"] = raw[i].numpy()
+    out["detect.y"] = y.numpy()
+    print("module detect", tuple(y.shape))
+    np.savez_compressed(GOLD / "modules.npz", **out)
+
+
+def nms_cases():
+    g = np.random.default_rng(7)
+    cases = []
+
+    def rand_boxes(n, span=640.0, wh=(8, 256)):
+        xy = g.uniform(0, span, (n, 2))
+        s = g.uniform(wh[0], wh[1], (n, 2))
+        return np.concatenate([xy - s / 2, xy + s / 2], 1).astype(np.float32)
+
+    for n in (1, 2, 7, 64, 200, 400, 1000):
+        for thr in (0.45, 0.5, 0.7):
+            b = rand_boxes(n)
+            # near-duplicate clusters
+            k = max(1, n // 4)
+            src = g.integers(0, n, k)
+            b[:k] = b[src] + g.normal(0, 2.0, (k, 4)).astype(np.float32)
+            s = g.uniform(0, 1, n).astype(np.float32)
+            if n > 4:  # exact score ties
+                s[g.integers(0, n, n // 3)] = s[0]
+            cases.append((b, s, thr))
+    # class-offset style boxes (fp32 cls * 7680)
+    b = rand_boxes(300)
+    cls = g.integers(0, 80, (300, 1)).astype(np.float32)
+    cases.append(((b + cls * np.float32(7680)).astype(np.float32), g.uniform(0, 1, 300).astype(np.float32), 0.7))
+    # known-answer probes
+    a_ = [0, 0, 10, 10]
+    cases.append((np.array([a_, [20, 20, 30, 30], a_], np.float32), np.array([0.5, 0.5, 0.5], np.float32), 0.5))
+    cases.append((np.array([[0, 0, 10, 10], [0, 0, 10, 5]], np.float32), np.array([0.9, 0.8], np.float32), 0.5))  # IoU == thr
+    cases.append((np.array([[0, 0, 3, 1], [0, 0, 1, 1]], np.float32), np.array([0.9, 0.8], np.float32), 1.0 / 3.0))
+    cases.append((np.array([[5, 5, 5, 5], [5, 5, 5, 5]], np.float32), np.array([0.9, 0.8], np.float32), 0.5))  # NaN IoU
+    cases.append((np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5))
+    return cases
+
+
+def gen_nms_torchvision():
+    import torchvision
+
+    out = {"n_cases": np.array(0)}
+    cases = nms_cases()
+    for i, (b, s, thr) in enumerate(cases):
+        keep = torchvision.ops.nms(torch.from_numpy(b), torch.from_numpy(s), thr).numpy()
+        out[f"c{i}.boxes"], out[f"c{i}.scores"], out[f"c{i}.thr"], out[f"c{i}.keep"] = b, s, np.array(thr), keep
+    out["n_cases"] = np.array(len(cases))
+    out["torchvision_version"] = np.array(torchvision.__version__)
+    np.savez_compressed(GOLD / "nms_torchvision.npz", **out)
+    print("nms_torchvision", len(cases), "cases")
+
+
+def synth_pred(B, A, nc, seed, mean, std):
+    """(B, 4+nc, A) fp32: cx,cy~U(0,640), w,h~U(8,256), scores = sigmoid(N(mean, std))."""
+    g = np.random.default_rng(seed)
+    p = np.empty((B, 4 + nc, A), np.float32)
+    p[:, 0:2] = g.uniform(0, 640, (B, 2, A))
+    p[:, 2:4] = g.uniform(8, 256, (B, 2, A))
+    p[:, 4:] = 1.0 / (1.0 + np.exp(-g.normal(mean, std, (B, nc, A))))
+    # clusters of near-duplicate boxes so that suppression actually happens
+    k = A // 3
+    src = g.integers(0, A, k)
+    p[:, 0:4, :k] = p[:, 0:4, src] + g.normal(0, 1.5, (B, 4, k)).astype(np.float32)
+    return p
+
+
+def gen_nms_reference():
+    import_reference()
+    from yololite.utils import ops
+
+    out = {}
+    specs = [
+        dict(tag="single_conf25", mean=-3.0, std=2.0, kw=dict(conf_thres=0.25, iou_thres=0.7)),
+        dict(tag="single_conf001", mean=-5.0, std=2.0, kw=dict(conf_thres=0.001, iou_thres=0.7)),
+        dict(tag="multi_conf001", mean=-7.0, std=2.0, kw=dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),
+        dict(tag="agnostic", mean=-3.0, std=2.0, kw=dict(conf_thres=0.25, iou_thres=0.45, agnostic=True)),
+        dict(tag="classes", mean=-3.0, std=2.0, kw=dict(conf_thres=0.1, iou_thres=0.6, classes=[0, 3, 17, 79])),
+        dict(tag="maxdet", mean=-2.0, std=2.0, kw=dict(conf_thres=0.05, iou_thres=0.9, max_det=20)),
+    ]
+    for i, sp in enumerate(specs):
+        pred = synth_pred(2, 420, 80, 50 + i, sp["mean"], sp["std"])
+        res = ops.non_max_suppression(torch.from_numpy(pred.copy()), max_time_img=1e9, **sp["kw"])
+        out[f"{sp['tag']}.pred"] = pred
+        out[f"{sp['tag']}.counts"] = np.array([len(r) for r in res])
+        out[f"{sp['tag']}.dets"] = np.concatenate([r.numpy() for r in res], 0) if res else np.zeros((0, 6), np.float32)
+        out[f"{sp['tag']}.kw"] = np.array(repr(sp["kw"]))
+        print("nms_reference", sp["tag"], out[f"{sp['tag']}.counts"])
+    np.savez_compressed(GOLD / "nms_reference.npz", **out)
+
+
+if __name__ == "__main__":
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_nms_torchvision()
+    gen_nms_reference()
+    gen_modules()
+    gen_models()

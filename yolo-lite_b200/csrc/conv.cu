@@ -1,0 +1,35 @@
+// C-ABI dispatch for the dense convolution: tcgen05 implicit GEMM when the problem fits, otherwise the
+// direct CUDA-core kernel (3-channel stem, odd sizes).  Both are this library's own sm_100a kernels;
+// there is no library or CPU fallback.
+#include "common.cuh"
+
+namespace yl {
+bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len);
+int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream);
+int launch_conv_direct(const yl_conv_args* a, cudaStream_t stream);
+}  // namespace yl
+
+extern "C" {
+
+int yl_conv_tc_supported(const yl_conv_args* a) {
+    if (!a) return 0;
+    return yl::conv_tc_supported(a, nullptr, 0) ? 1 : 0;
+}
+
+int yl_conv_bn_act(const yl_conv_args* a, void* stream) {
+    YL_CHECK(a != nullptr, YL_ERR_ARG, "null conv args");
+    YL_CHECK(a->x.data && a->y.data && a->w && a->bias, YL_ERR_ARG, "null tensor pointer");
+    YL_CHECK(a->x.c > 0 && a->y.c > 0 && a->x.n > 0 && a->x.h > 0 && a->x.w > 0, YL_ERR_ARG, "empty tensor");
+    YL_CHECK(a->x.coff + a->x.c <= a->x.cstride && a->y.coff + a->y.c <= a->y.cstride, YL_ERR_ARG,
+             "channel slice exceeds buffer");
+    if (a->res.data) {
+        YL_CHECK(a->res.c == a->y.c && a->res.coff + a->res.c <= a->res.cstride, YL_ERR_ARG, "residual slice mismatch");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->impl == YL_IMPL_DIRECT) return yl::launch_conv_direct(a, s);
+    if (a->impl == YL_IMPL_TCGEN05) return yl::launch_conv_tc(a, s);
+    if (yl::conv_tc_supported(a, nullptr, 0)) return yl::launch_conv_tc(a, s);
+    return yl::launch_conv_direct(a, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,642 @@
+// Batched non-max suppression on the GPU, bit-exact against the reference's CPU path
+// (utils/ops.py:138-273 + torchvision.ops.nms CPU kernel).
+//
+// Kernel 1  nms_filter_kernel   HBM-bound sweep over the (B, 4+nc, A) prediction tensor, coalesced along the
+//                               anchor axis (float4 per thread).  Confidence test (strict >), best class or
+//                               multi-label expansion, optional class filter, warp-ballot aggregated
+//                               compaction.  A candidate is one 64-bit key
+//                                   key = (~ordered(score)) << 32 | (anchor * nc + class)
+//                               so ascending key order == descending score with ties broken by the
+//                               reference's row order (== stable descending sort), and every key is unique:
+//                               the result is independent of the (atomic) compaction order.
+// Kernel 2  nms_select_kernel   one CTA per image: shared-memory bitonic sort of the keys (radix-select
+//                               rounds first when there are more than SORT_CAP candidates, which also
+//                               implements the max_nms top-k), then greedy suppression in sorted order:
+//                               512 candidates at a time are tested against the kept list, survivors are
+//                               compacted, their pairwise IoU bitmask is staged in shared memory and one
+//                               warp resolves it serially; stops at max_det survivors.
+// IoU arithmetic follows torchvision's CPU kernel operation by operation (no FMA contraction, same
+// std::max/std::min operand order, fp32 IoU compared against the double threshold).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace yl {
+
+constexpr int kSelThreads = 1024;
+constexpr int kSortCap = 16384;  // keys sorted in shared memory per round
+constexpr int kChunk = 512;      // candidates resolved per bitmask round
+constexpr int kMaskWords = kChunk / 32;
+
+__device__ __forceinline__ uint32_t score_to_desc(float s) {
+    uint32_t b = __float_as_uint(s);
+    uint32_t ordered = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    return ~ordered;
+}
+__device__ __forceinline__ float desc_to_score(uint32_t d) {
+    uint32_t ordered = ~d;
+    uint32_t b = ordered ^ ((ordered >> 31) ? 0x80000000u : 0xffffffffu);
+    return __uint_as_float(b);
+}
+
+// ---------------------------------------------------------------------------------------------- filter
+template <int VEC, bool MULTI>
+__global__ void __launch_bounds__(256) nms_filter_kernel(const float* __restrict__ pred, int nc, int A, float conf,
+                                                         const int32_t* __restrict__ classes, int n_classes,
+                                                         unsigned long long cap,
+                                                         uint32_t* __restrict__ counts,
+                                                         unsigned long long* __restrict__ keys) {
+    __shared__ uint32_t cmask[32];  // class filter bitmask (nc <= 1024)
+    const int b = blockIdx.y;
+    if (n_classes > 0) {
+        if (threadIdx.x < 32) cmask[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_classes; i += blockDim.x) {
+            const int c = classes[i];
+            if (c >= 0 && c < nc) atomicOr(&cmask[c >> 5], 1u << (c & 31));
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const bool in_range = a0 < A;
+    const float* base = pred + ((long long)b * (4 + nc) + 4) * A + a0;
+    unsigned long long* kout = keys + (unsigned long long)b * cap;
+
+    float best[VEC];
+    int bestc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        best[v] = -INFINITY;
+        bestc[v] = 0;
+    }
+
+#pragma unroll 8
+    for (int c = 0; c < nc; ++c) {
+        float s[VEC];
+        if (in_range) {
+            if (VEC == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(base + (long long)c * A));
+                s[0] = t.x; s[1 % VEC] = t.y; s[2 % VEC] = t.z; s[3 % VEC] = t.w;
+            } else {
+                s[0] = __ldg(base + (long long)c * A);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) s[v] = -INFINITY;
+        }
+        if (!MULTI) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (s[v] > best[v]) {  // strict: ties keep the lowest class index (torch.max)
+                    best[v] = s[v];
+                    bestc[v] = c;
+                }
+        } else {
+            const bool cls_ok = n_classes == 0 || ((cmask[c >> 5] >> (c & 31)) & 1u);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const bool emit = in_range && cls_ok && (s[v] > conf);
+                const unsigned m = __ballot_sync(0xffffffffu, emit);
+                if (m) {
+                    uint32_t pos0 = 0;
+                    if (lane == 0) pos0 = atomicAdd(&counts[b], (uint32_t)__popc(m));
+                    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                    if (emit) {
+                        const uint32_t idx = (uint32_t)(a0 + v) * (uint32_t)nc + (uint32_t)c;
+                        kout[pos0 + __popc(m & ((1u << lane) - 1u))] =
+                            ((unsigned long long)score_to_desc(s[v]) << 32) | idx;
+                    }
+                }
+            }
+        }
+    }
+    if (!MULTI) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            bool emit = in_range && (best[v] > conf);
+            if (emit && n_classes > 0) emit = (cmask[bestc[v] >> 5] >> (bestc[v] & 31)) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, emit);
+            if (m) {
+                uint32_t pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(&counts[b], (uint32_t)__popc(m));
+                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                if (emit) {
+                    const uint32_t idx = (uint32_t)(a0 + v) * (uint32_t)nc + (uint32_t)bestc[v];
+                    kout[pos0 + __popc(m & ((1u << lane) - 1u))] =
+                        ((unsigned long long)score_to_desc(best[v]) << 32) | idx;
+                }
+            }
+        }
+    }
+}
+
+// keys for yl_nms_boxes: every box is a candidate
+__global__ void nms_boxes_keys_kernel(const float* __restrict__ scores, int n, unsigned long long* __restrict__ keys,
+                                      uint32_t* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)score_to_desc(scores[i]) << 32) | (uint32_t)i;
+    if (i == 0) counts[0] = (uint32_t)n;
+}
+
+// ---------------------------------------------------------------------------------------------- select
+struct SelParams {
+    const float* pred;   // MODE 0: (B, 4+nc, A) xywh+scores.  MODE 1: boxes (n,4) xyxy
+    int nc, A;
+    unsigned long long cap;
+    const uint32_t* counts;
+    const unsigned long long* keys;
+    float thr;           // largest float <= double iou threshold
+    float max_wh;        // class offset scale (0 when agnostic)
+    int max_det, max_nms;
+    int kept_in_smem;
+    float* kept_ws;      // global kept-list storage when max_det is large: [B][max_det][5] + keys
+    unsigned long long* kept_keys_ws;
+    float* out;          // MODE 0: (B, max_det, 6)
+    int32_t* out_counts;
+    long long* keep;     // MODE 1: int64[n]
+};
+
+// torchvision CPU: suppressed iff inter / (area_i + area_j - inter) > thr, i = kept (earlier) box.
+__device__ __forceinline__ bool iou_suppresses(const float4 bi, float ai, const float4 bj, float aj, float thr) {
+    const float xx1 = (bi.x < bj.x) ? bj.x : bi.x;  // std::max(ix1, x1[j])
+    const float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
+    const float xx2 = (bj.z < bi.z) ? bj.z : bi.z;  // std::min(ix2, x2[j])
+    const float yy2 = (bj.w < bi.w) ? bj.w : bi.w;
+    const float dw = __fsub_rn(xx2, xx1), dh = __fsub_rn(yy2, yy1);
+    const float w = (0.f < dw) ? dw : 0.f;  // std::max(0, xx2 - xx1)
+    const float h = (0.f < dh) ? dh : 0.f;
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+    return ovr > thr;
+}
+
+template <int MODE>
+__device__ __forceinline__ void fetch_box(const SelParams& p, int b, unsigned long long key, float4* raw, float4* off,
+                                          float* area, float* score, int* cls) {
+    const uint32_t idx = (uint32_t)(key & 0xffffffffull);
+    *score = desc_to_score((uint32_t)(key >> 32));
+    if (MODE == 0) {
+        const int a = (int)(idx / (uint32_t)p.nc);
+        const int c = (int)(idx - (uint32_t)a * (uint32_t)p.nc);
+        const float* q = p.pred + (long long)b * (4 + p.nc) * p.A + a;
+        const float cx = __ldg(q), cy = __ldg(q + p.A), w = __ldg(q + 2 * (long long)p.A),
+                    h = __ldg(q + 3 * (long long)p.A);
+        const float hw = w * 0.5f, hh = h * 0.5f;  // x[..., 2:] / 2 (exact)
+        raw->x = __fsub_rn(cx, hw);
+        raw->y = __fsub_rn(cy, hh);
+        raw->z = __fadd_rn(cx, hw);
+        raw->w = __fadd_rn(cy, hh);
+        const float o = __fmul_rn((float)c, p.max_wh);  // x[:, 5:6] * max_wh
+        off->x = __fadd_rn(raw->x, o);
+        off->y = __fadd_rn(raw->y, o);
+        off->z = __fadd_rn(raw->z, o);
+        off->w = __fadd_rn(raw->w, o);
+        *cls = c;
+    } else {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.pred) + idx);
+        *raw = t;
+        *off = t;
+        *cls = 0;
+    }
+    *area = __fmul_rn(__fsub_rn(off->z, off->x), __fsub_rn(off->w, off->y));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelParams p) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);              // [kSortCap]
+    uint32_t* mask = reinterpret_cast<uint32_t*>(skeys + kSortCap);                    // [kChunk][kMaskWords]
+    float4* cbox = reinterpret_cast<float4*>(mask + kChunk * kMaskWords);              // [kChunk] compacted
+    float* carea = reinterpret_cast<float*>(cbox + kChunk);                            // [kChunk]
+    int* csrc = reinterpret_cast<int*>(carea + kChunk);                                // [kChunk]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(csrc + kChunk);                       // [256]
+    int* misc = reinterpret_cast<int*>(hist + 256);                                    // [64]
+    unsigned long long* misc64 = reinterpret_cast<unsigned long long*>(misc + 64);     // [4]
+    float* kept_sm = reinterpret_cast<float*>(misc64 + 4);                             // [max_det][5] (optional)
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long* gkeys = p.keys + (unsigned long long)b * p.cap;
+    unsigned long long n64 = p.counts[b];
+    if (n64 > p.cap) n64 = p.cap;
+    const int n = (int)n64;
+    const int n_proc = n < p.max_nms ? n : p.max_nms;
+
+    float* kept = p.kept_in_smem ? kept_sm : (p.kept_ws + (long long)b * p.max_det * 5);
+    unsigned long long* kept_keys =
+        p.kept_in_smem ? reinterpret_cast<unsigned long long*>(kept_sm + (size_t)p.max_det * 5 + (p.max_det & 1))
+                       : (p.kept_keys_ws + (long long)b * p.max_det);
+
+    int nk = 0;          // kept so far (uniform across the block)
+    int processed = 0;   // candidates consumed in sorted order
+    unsigned long long lo = 0;  // keys <= lo are already consumed (radix rounds)
+    const bool single_round = n <= kSortCap;
+
+    while (processed < n_proc && nk < p.max_det) {
+        int m = n_proc - processed;
+        if (m > kSortCap) m = kSortCap;
+        // ---------------- stage the next m keys (ascending) into shared memory
+        if (single_round) {
+            for (int i = tid; i < n; i += kSelThreads) skeys[i] = gkeys[i];
+            int P = 32;
+            while (P < n) P <<= 1;
+            for (int i = n + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < P; i += kSelThreads) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned long long x = skeys[i], y = skeys[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((x > y) == up) {
+                                skeys[i] = y;
+                                skeys[ixj] = x;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+        } else {
+            // radix select: T = m-th smallest key among keys > lo (8 passes of 8 bits, MSD first)
+            unsigned long long prefix = 0, pmask = 0;
+            int remaining = m;
+            for (int pass = 0; pass < 8; ++pass) {
+                const int shift = 56 - 8 * pass;
+                if (tid < 256) hist[tid] = 0;
+                __syncthreads();
+                for (int i = tid; i < n; i += kSelThreads) {
+                    const unsigned long long k = gkeys[i];
+                    if (k > lo && (k & pmask) == prefix) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xffu], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int acc = 0, d = 0;
+                    for (; d < 256; ++d) {
+                        const int c = (int)hist[d];
+                        if (acc + c >= remaining) break;
+                        acc += c;
+                    }
+                    misc[0] = d;
+                    misc[1] = remaining - acc;
+                }
+                __syncthreads();
+                prefix |= (unsigned long long)misc[0] << shift;
+                pmask |= 0xffull << shift;
+                remaining = misc[1];
+                __syncthreads();
+            }
+            const unsigned long long T = prefix;
+            if (tid == 0) misc[2] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += kSelThreads) {
+                const unsigned long long k = gkeys[i];
+                if (k > lo && k <= T) skeys[atomicAdd(&misc[2], 1)] = k;
+            }
+            __syncthreads();
+            // exactly m keys were gathered (keys are unique); sort them
+            int P = 32;
+            while (P < m) P <<= 1;
+            for (int i = m + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < P; i += kSelThreads) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned long long x = skeys[i], y = skeys[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((x > y) == up) {
+                                skeys[i] = y;
+                                skeys[ixj] = x;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            lo = T;
+        }
+
+        // ---------------- greedy suppression over skeys[0..m) in chunks
+        for (int s0 = 0; s0 < m && nk < p.max_det; s0 += kChunk) {
+            const int cnt = (m - s0) < kChunk ? (m - s0) : kChunk;
+            // 1. candidate vs kept list
+            float4 ob = make_float4(0, 0, 0, 0), rb;
+            float ar = 0.f, sc;
+            int cl;
+            bool alive = false;
+            if (tid < cnt) {
+                fetch_box<MODE>(p, b, skeys[s0 + tid], &rb, &ob, &ar, &sc, &cl);
+                alive = true;
+                for (int i = 0; i < nk; ++i) {
+                    const float4 kb = make_float4(kept[i * 5 + 0], kept[i * 5 + 1], kept[i * 5 + 2], kept[i * 5 + 3]);
+                    if (iou_suppresses(kb, kept[i * 5 + 4], ob, ar, p.thr)) {
+                        alive = false;
+                        break;
+                    }
+                }
+            }
+            // 2. ordered compaction of survivors
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) misc[8 + warp] = __popc(bal);
+            __syncthreads();
+            if (warp == 0) {
+                int v = misc[8 + lane];
+                int incl = v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                misc[8 + lane] = incl - v;  // exclusive
+                if (lane == 31) misc[3] = incl;
+            }
+            __syncthreads();
+            const int L = misc[3];
+            if (alive) {
+                const int pos = misc[8 + warp] + __popc(bal & ((1u << lane) - 1u));
+                cbox[pos] = ob;
+                carea[pos] = ar;
+                csrc[pos] = s0 + tid;
+            }
+            __syncthreads();
+            // 3. pairwise bitmask among survivors (upper triangle)
+            const int W = (L + 31) >> 5;
+            for (int e = tid; e < L * W; e += kSelThreads) {
+                const int i = e / W, wd = e - i * W;
+                uint32_t bits = 0;
+                if (wd >= (i >> 5)) {
+                    const float4 bi = cbox[i];
+                    const float ai = carea[i];
+                    const int j0 = wd << 5;
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int j = j0 + jj;
+                        if (j > i && j < L && iou_suppresses(bi, ai, cbox[j], carea[j], p.thr)) bits |= 1u << jj;
+                    }
+                }
+                mask[i * kMaskWords + wd] = bits;
+            }
+            __syncthreads();
+            // 4. serial resolve by warp 0: lane l owns word l of the removed set
+            if (warp == 0) {
+                uint32_t rem = 0;
+                int cur = 0;
+                int nk_l = nk;
+                while (nk_l < p.max_det) {
+                    // first index >= cur that is valid and not removed
+                    uint32_t cand = 0;
+                    if (lane < W) {
+                        cand = ~rem;
+                        const int lo_i = lane << 5;
+                        if (L - lo_i < 32) cand &= (L - lo_i <= 0) ? 0u : ((1u << (L - lo_i)) - 1u);
+                        if (cur > lo_i) cand &= (cur - lo_i >= 32) ? 0u : ~((1u << (cur - lo_i)) - 1u);
+                    }
+                    const unsigned has = __ballot_sync(0xffffffffu, cand != 0);
+                    if (!has) break;
+                    const int src_lane = __ffs(has) - 1;
+                    const uint32_t cw = __shfl_sync(0xffffffffu, cand, src_lane);
+                    const int i = (src_lane << 5) + (__ffs(cw) - 1);
+                    if (lane < W) rem |= mask[i * kMaskWords + lane];
+                    if (lane == 0) {
+                        const float4 bb = cbox[i];
+                        kept[nk_l * 5 + 0] = bb.x;
+                        kept[nk_l * 5 + 1] = bb.y;
+                        kept[nk_l * 5 + 2] = bb.z;
+                        kept[nk_l * 5 + 3] = bb.w;
+                        kept[nk_l * 5 + 4] = carea[i];
+                        kept_keys[nk_l] = skeys[csrc[i]];
+                    }
+                    ++nk_l;
+                    cur = i + 1;
+                }
+                if (lane == 0) misc[4] = nk_l;
+            }
+            __threadfence_block();
+            __syncthreads();
+            nk = misc[4];
+            __syncthreads();
+        }
+        processed += m;
+    }
+
+    // ---------------- emit
+    if (MODE == 0) {
+        float* o = p.out + (long long)b * p.max_det * 6;
+        for (int r = tid; r < p.max_det; r += kSelThreads) {
+            float4 rb = make_float4(0, 0, 0, 0), ob;
+            float ar, sc = 0.f;
+            int cl = 0;
+            if (r < nk) fetch_box<0>(p, b, kept_keys[r], &rb, &ob, &ar, &sc, &cl);
+            o[r * 6 + 0] = rb.x;
+            o[r * 6 + 1] = rb.y;
+            o[r * 6 + 2] = rb.z;
+            o[r * 6 + 3] = rb.w;
+            o[r * 6 + 4] = sc;
+            o[r * 6 + 5] = (float)cl;
+        }
+        if (tid == 0) p.out_counts[b] = nk;
+    } else {
+        for (int r = tid; r < nk; r += kSelThreads) p.keep[r] = (long long)(kept_keys[r] & 0xffffffffull);
+        if (tid == 0) p.out_counts[0] = nk;
+    }
+}
+
+static size_t sel_smem_bytes(int max_det, bool kept_in_smem) {
+    size_t s = (size_t)kSortCap * 8 + (size_t)kChunk * kMaskWords * 4 + (size_t)kChunk * (16 + 4 + 4) + 256 * 4 +
+               64 * 4 + 4 * 8;
+    if (kept_in_smem) s += ((size_t)max_det * 5 + (max_det & 1)) * 4 + (size_t)max_det * 8 + 16;
+    return s;
+}
+
+static int g_sel_max_smem = 0;
+
+int init_nms() {
+    int dev = 0;
+    YL_CUDA(cudaGetDevice(&dev));
+    YL_CUDA(cudaDeviceGetAttribute(&g_sel_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    YL_CUDA(cudaFuncSetAttribute(nms_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_sel_max_smem));
+    YL_CUDA(cudaFuncSetAttribute(nms_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_sel_max_smem));
+    return YL_OK;
+}
+
+static float thr_to_float(double thr) {
+    // largest float f with (double)f <= thr: then  (double)ovr > thr  <=>  ovr > f  for every float ovr
+    float f = (float)thr;
+    if ((double)f > thr) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void xywh2xyxy_kernel(float* __restrict__ pred, int C, int A, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int a = (int)(i % A);
+    const long long b = i / A;
+    float* q = pred + b * C * A + a;
+    const float cx = q[0], cy = q[A], hw = q[2 * (long long)A] * 0.5f, hh = q[3 * (long long)A] * 0.5f;
+    q[0] = __fsub_rn(cx, hw);
+    q[A] = __fsub_rn(cy, hh);
+    q[2 * (long long)A] = __fadd_rn(cx, hw);
+    q[3 * (long long)A] = __fadd_rn(cy, hh);
+}
+
+__global__ void scale_boxes_kernel(float* __restrict__ dets, const int32_t* __restrict__ counts, int max_det,
+                                   const float* __restrict__ params) {
+    const int b = blockIdx.x;
+    const float gain = params[b * 5 + 0], padx = params[b * 5 + 1], pady = params[b * 5 + 2], w0 = params[b * 5 + 3],
+                h0 = params[b * 5 + 4];
+    const int n = counts[b];
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        float* d = dets + ((long long)b * max_det + r) * 6;
+        // ops.scale_boxes: subtract pad, divide by gain (true division), clip_boxes clamp
+        float x1 = __fdiv_rn(__fsub_rn(d[0], padx), gain), y1 = __fdiv_rn(__fsub_rn(d[1], pady), gain);
+        float x2 = __fdiv_rn(__fsub_rn(d[2], padx), gain), y2 = __fdiv_rn(__fsub_rn(d[3], pady), gain);
+        d[0] = fminf(fmaxf(x1, 0.f), w0);
+        d[1] = fminf(fmaxf(y1, 0.f), h0);
+        d[2] = fminf(fmaxf(x2, 0.f), w0);
+        d[3] = fminf(fmaxf(y2, 0.f), h0);
+    }
+}
+
+}  // namespace yl
+
+extern "C" {
+
+size_t yl_nms_workspace_bytes(int B, int A, int nc, int multi_label) {
+    if (B <= 0 || A <= 0 || nc <= 0) return 0;
+    const size_t cap = multi_label ? (size_t)A * nc : (size_t)A;
+    size_t s = yl::align_up((size_t)B * 4, 256);   // candidate counters
+    s += yl::align_up((size_t)B * cap * 8, 256);   // keys
+    return s;
+}
+
+int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, double iou_thres,
+                   const int32_t* classes_dev, int n_classes, int agnostic, int multi_label, int max_det, int max_nms,
+                   float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* counts, void* stream) {
+    YL_CHECK(pred && out && counts && workspace, YL_ERR_ARG, "null pointer");
+    YL_CHECK(B > 0 && nc > 0 && nc <= 1024 && A > 0, YL_ERR_ARG, "bad dims B=%d nc=%d A=%d", B, nc, A);
+    YL_CHECK((long long)A * nc < (1ll << 32), YL_ERR_ARG, "A*nc must fit 32 bits");
+    YL_CHECK(max_det > 0 && max_det <= 1024, YL_ERR_ARG, "max_det must be in [1,1024]");
+    YL_CHECK(max_nms > 0, YL_ERR_ARG, "max_nms must be positive");
+    YL_CHECK(conf_thres >= 0.f && conf_thres <= 1.f && iou_thres >= 0. && iou_thres <= 1., YL_ERR_ARG,
+             "thresholds must be in [0,1]");
+    YL_CHECK(n_classes == 0 || classes_dev, YL_ERR_ARG, "classes_dev is NULL");
+    const size_t need = yl_nms_workspace_bytes(B, A, nc, multi_label);
+    YL_CHECK(workspace_bytes >= need, YL_ERR_WORKSPACE, "NMS workspace too small: %zu < %zu", workspace_bytes, need);
+    cudaStream_t s = (cudaStream_t)stream;
+    multi_label = multi_label && nc > 1;
+
+    const size_t cap = multi_label ? (size_t)A * nc : (size_t)A;
+    uint32_t* cand_counts = reinterpret_cast<uint32_t*>(workspace);
+    unsigned long long* keys =
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + yl::align_up((size_t)B * 4, 256));
+    YL_CUDA(cudaMemsetAsync(cand_counts, 0, (size_t)B * 4, s));
+
+    const bool vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
+    {
+        dim3 grid((unsigned)yl::ceil_div(A, vec4 ? 256 * 4 : 256), (unsigned)B, 1);
+#define YL_FILTER(V, M)                                                                                      \
+    yl::nms_filter_kernel<V, M><<<grid, 256, 0, s>>>(pred, nc, A, conf_thres, classes_dev, n_classes,          \
+                                                     (unsigned long long)cap, cand_counts, keys)
+        if (vec4 && multi_label) YL_FILTER(4, true);
+        else if (vec4) YL_FILTER(4, false);
+        else if (multi_label) YL_FILTER(1, true);
+        else YL_FILTER(1, false);
+#undef YL_FILTER
+    }
+    YL_LAUNCH_OK("nms_filter_kernel");
+
+    yl::SelParams p;
+    p.pred = pred;
+    p.nc = nc;
+    p.A = A;
+    p.cap = cap;
+    p.counts = cand_counts;
+    p.keys = keys;
+    p.thr = yl::thr_to_float(iou_thres);
+    p.max_wh = agnostic ? 0.f : max_wh;
+    p.max_det = max_det;
+    p.max_nms = max_nms;
+    p.kept_in_smem = 1;
+    p.kept_ws = nullptr;
+    p.kept_keys_ws = nullptr;
+    p.out = out;
+    p.out_counts = counts;
+    p.keep = nullptr;
+    const size_t smem = yl::sel_smem_bytes(max_det, true);
+    YL_CHECK((int)smem <= yl::g_sel_max_smem, YL_ERR_UNSUPPORTED, "NMS needs %zu B shared memory (yl_init called?)",
+             smem);
+    yl::nms_select_kernel<0><<<B, yl::kSelThreads, smem, s>>>(p);
+    YL_LAUNCH_OK("nms_select_kernel");
+    return YL_OK;
+}
+
+size_t yl_nms_boxes_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    return 256 + yl::align_up((size_t)n * 8, 256) + yl::align_up((size_t)n * 5 * 4, 256) +
+           yl::align_up((size_t)n * 8, 256);
+}
+
+int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thres, void* workspace,
+                 size_t workspace_bytes, int64_t* keep, int32_t* count, void* stream) {
+    YL_CHECK(count && workspace, YL_ERR_ARG, "null pointer");
+    YL_CHECK(n >= 0, YL_ERR_ARG, "negative n");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        YL_CUDA(cudaMemsetAsync(count, 0, 4, s));
+        return YL_OK;
+    }
+    YL_CHECK(boxes && scores && keep, YL_ERR_ARG, "null pointer");
+    YL_CHECK((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, YL_ERR_ARG, "boxes must be 16-byte aligned");
+    YL_CHECK(workspace_bytes >= yl_nms_boxes_workspace_bytes(n), YL_ERR_WORKSPACE, "NMS workspace too small");
+    char* ws = reinterpret_cast<char*>(workspace);
+    uint32_t* cand_counts = reinterpret_cast<uint32_t*>(ws);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + 256);
+    float* kept_ws = reinterpret_cast<float*>(ws + 256 + yl::align_up((size_t)n * 8, 256));
+    unsigned long long* kept_keys_ws = reinterpret_cast<unsigned long long*>(
+        ws + 256 + yl::align_up((size_t)n * 8, 256) + yl::align_up((size_t)n * 5 * 4, 256));
+    yl::nms_boxes_keys_kernel<<<yl::ceil_div(n, 256), 256, 0, s>>>(scores, n, keys, cand_counts);
+    YL_LAUNCH_OK("nms_boxes_keys_kernel");
+
+    yl::SelParams p;
+    p.pred = boxes;
+    p.nc = 1;
+    p.A = n;
+    p.cap = (unsigned long long)n;
+    p.counts = cand_counts;
+    p.keys = keys;
+    p.thr = yl::thr_to_float(iou_thres);
+    p.max_wh = 0.f;
+    p.max_det = n;
+    p.max_nms = n;
+    p.kept_in_smem = 0;
+    p.kept_ws = kept_ws;
+    p.kept_keys_ws = kept_keys_ws;
+    p.out = nullptr;
+    p.out_counts = count;
+    p.keep = reinterpret_cast<long long*>(keep);
+    const size_t smem = yl::sel_smem_bytes(0, false);
+    YL_CHECK((int)smem <= yl::g_sel_max_smem, YL_ERR_UNSUPPORTED, "NMS needs %zu B shared memory (yl_init called?)",
+             smem);
+    yl::nms_select_kernel<1><<<1, yl::kSelThreads, smem, s>>>(p);
+    YL_LAUNCH_OK("nms_select_kernel");
+    return YL_OK;
+}
+
+int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream) {
+    YL_CHECK(pred && B > 0 && C >= 4 && A > 0, YL_ERR_ARG, "bad arguments");
+    const long long total = (long long)B * A;
+    yl::xywh2xyxy_kernel<<<(unsigned)yl::ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(pred, C, A, total);
+    YL_LAUNCH_OK("xywh2xyxy_kernel");
+    return YL_OK;
+}
+
+int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream) {
+    YL_CHECK(dets && counts && params_dev && B > 0 && max_det > 0, YL_ERR_ARG, "bad arguments");
+    yl::scale_boxes_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(dets, counts, max_det, params_dev);
+    YL_LAUNCH_OK("scale_boxes_kernel");
+    return YL_OK;
+}
+
+}  // extern "C"
