@@ -281,7 +281,6 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
     if (y.c % 8 || y.coff % 8 || y.cstride % 8) NOPE("output channels/offset/stride must be multiples of 8");
     if (a->ci_pad % 8 || a->ci_pad < x.c) NOPE("ci_pad must be a multiple of 8 and >= x.c");
     if (a->co_pad % 8 || a->co_pad < y.c) NOPE("co_pad must be a multiple of 8 and >= y.c");
-    if (x.c < 16) NOPE("fewer than 16 input channels (stem): direct kernel");
     if (a->stride == 2 && ((x.h | x.w) & 1)) NOPE("stride 2 needs even input dims");
     if (a->res.data && (a->res.c % 8 || a->res.coff % 8 || a->res.cstride % 8 || a->res.dtype != YL_BF16))
         NOPE("residual must be bf16 with 8-channel alignment");

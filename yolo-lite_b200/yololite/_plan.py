@@ -1,0 +1,173 @@
+"""Static launch plans: the host-side "graph executor" of the B200 path.
+
+A `Builder` records, for one fixed input shape, the exact sequence of C-ABI kernel launches a module tree
+performs, with every activation buffer pre-allocated (NHWC bf16) and channel concatenation expressed as
+aliasing (producers write straight into channel slices of the consumer's buffer).  `Plan.run()` replays the
+pre-marshalled ctypes calls on the current stream; `Plan.capture()` wraps that replay in a CUDA graph so a
+forward is one `cudaGraphLaunch` (the reference issues ~300 ATen kernels per forward, nn/tasks.py:118-145).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable
+
+import torch
+
+from . import _C, _ops
+from ._ops import PackedConv, View
+
+
+class Dest:
+    """Deferred output placement: resolves to a View once the producer knows its output shape."""
+
+    def __init__(self, resolve: Callable[[int, int, int, int], View]):
+        self._resolve = resolve
+
+    def __call__(self, n, h, w, c) -> View:
+        v = self._resolve(n, h, w, c)
+        assert (v.n, v.h, v.w, v.c) == (n, h, w, c), f"destination {(v.n, v.h, v.w, v.c)} != {(n, h, w, c)}"
+        return v
+
+
+class Builder:
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = _C.init(device)
+        self.calls: list[tuple] = []      # (fn, args tuple without stream, keepalive)
+        self.buffers: list[torch.Tensor] = []
+        self.bytes = 0
+
+    # ------------------------------------------------------------------ memory
+    def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
+        buf = torch.empty((n, h, w, c), dtype=dtype, device=self.device)
+        self.buffers.append(buf)
+        self.bytes += buf.numel() * buf.element_size()
+        return View(buf, 0, c)
+
+    def _out(self, out, n, h, w, c, dtype=torch.bfloat16) -> View:
+        if out is None:
+            return self.alloc(n, h, w, c, dtype)
+        if isinstance(out, Dest):
+            return out(n, h, w, c)
+        assert (out.n, out.h, out.w, out.c) == (n, h, w, c), ((out.n, out.h, out.w, out.c), (n, h, w, c))
+        return out
+
+    def _push(self, fn, *args, keep=()):
+        self.calls.append((fn, args, keep))
+
+    # ------------------------------------------------------------------ ops
+    def input_nchw(self, x_nchw_static: torch.Tensor) -> View:
+        n, c, h, w = x_nchw_static.shape
+        v = self.alloc(n, h, w, c)
+        t = v.ct()
+        self._push(self.lib.yl_nchw_to_nhwc, x_nchw_static.data_ptr(), C.byref(t), keep=(t, x_nchw_static))
+        return v
+
+    def conv(self, x: View, pc: PackedConv, stride=1, act=True, out=None, res: View | None = None,
+             upsample=False, out_dtype=torch.bfloat16, impl=_C.IMPL_AUTO) -> View:
+        k = pc.k
+        ho = (x.h + 2 * (k // 2) - k) // stride + 1
+        wo = (x.w + 2 * (k // 2) - k) // stride + 1
+        u = 2 if upsample else 1
+        y = self._out(out, x.n, ho * u, wo * u, pc.co, out_dtype)
+        if pc.depthwise:
+            assert stride == 1 and k == 3 and not upsample
+            xt, yt = x.ct(), y.ct()
+            rt = res.ct() if res is not None else None
+            self._push(self.lib.yl_dwconv3x3, C.byref(xt), C.byref(yt), pc.w.data_ptr(), pc.bias.data_ptr(), int(act),
+                       C.byref(rt) if rt is not None else None, keep=(xt, yt, rt, pc))
+            return y
+        a = _ops.conv_args(x, y, pc, stride, act, res, upsample, impl)
+        self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc))
+        return y
+
+    def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):
+        ts = [v.ct() for v in (x, y1, y2, y3)]
+        self._push(self.lib.yl_sppf_pool, *[C.byref(t) for t in ts], k, keep=tuple(ts))
+
+    def upsample2x(self, x: View, out=None) -> View:
+        y = self._out(out, x.n, 2 * x.h, 2 * x.w, x.c)
+        xt, yt = x.ct(), y.ct()
+        self._push(self.lib.yl_upsample2x, C.byref(xt), C.byref(yt), keep=(xt, yt))
+        return y
+
+    def copy(self, x: View, out=None) -> View:
+        y = self._out(out, x.n, x.h, x.w, x.c)
+        xt, yt = x.ct(), y.ct()
+        self._push(self.lib.yl_copy_slice, C.byref(xt), C.byref(yt), keep=(xt, yt))
+        return y
+
+    def attention(self, qkv: View, heads: int, key_dim: int, head_dim: int, scale: float, out=None) -> View:
+        y = self._out(out, qkv.n, qkv.h, qkv.w, heads * head_dim)
+        qt, yt = qkv.ct(), y.ct()
+        self._push(self.lib.yl_psa_attention, C.byref(qt), C.byref(yt), heads, key_dim, head_dim, float(scale),
+                   keep=(qt, yt))
+        return y
+
+    def detect_decode(self, levels: list[View], strides, reg_max: int, nc: int) -> torch.Tensor:
+        n = levels[0].n
+        a = sum(v.h * v.w for v in levels)
+        y = torch.empty((n, 4 + nc, a), dtype=torch.float32, device=self.device)
+        self.buffers.append(y)
+        arr = (_C.Tensor * len(levels))(*[v.ct() for v in levels])
+        st = (C.c_float * len(levels))(*[float(s) for s in strides])
+        self._push(self.lib.yl_detect_decode, arr, len(levels), st, reg_max, nc, y.data_ptr(), keep=(arr, st))
+        return y
+
+    def to_nchw(self, x: View) -> torch.Tensor:
+        out = torch.empty((x.n, x.c, x.h, x.w), dtype=torch.float32, device=self.device)
+        self.buffers.append(out)
+        xt = x.ct()
+        self._push(self.lib.yl_nhwc_to_nchw, C.byref(xt), out.data_ptr(), keep=(xt,))
+        return out
+
+    def finish(self) -> "Plan":
+        return Plan(self)
+
+
+class Plan:
+    """Replayable launch sequence (+ optional CUDA graph)."""
+
+    def __init__(self, b: Builder):
+        self.device = b.device
+        self.calls = b.calls
+        self.buffers = b.buffers
+        self.bytes = b.bytes
+        self.graph: torch.cuda.CUDAGraph | None = None
+        self.n_launches = len(b.calls)
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return
+        self.run_eager()
+
+    def run_eager(self, skip: int = 0):
+        s = _C.stream_ptr()
+        check = _C.check
+        for fn, args, _ in self.calls[skip:]:
+            rc = fn(*args, s)
+            if rc != 0:
+                check(rc, fn.__name__)
+
+    def capture(self, skip: int = 0):
+        """Capture calls[skip:] into a CUDA graph (calls[:skip] stay eager, e.g. the image ingest)."""
+        torch.cuda.synchronize(self.device)
+        self.run_eager()  # warm-up outside capture (lazy module loading, first-touch)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager(skip)
+        self.graph = g
+        self._skip = skip
+        if skip:
+            eager = self.calls[:skip]
+
+            def run():
+                s = _C.stream_ptr()
+                for fn, args, _ in eager:
+                    _C.check(fn(*args, s), fn.__name__)
+                g.replay()
+
+            self.run = run  # type: ignore[method-assign]
+        return self
