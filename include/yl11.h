@@ -122,6 +122,10 @@ int yl_psa_attention(const yl_tensor* qkv, const yl_tensor* out, int heads, int 
 int yl_detect_decode(const yl_tensor* levels, int nl, const float* strides_host, int reg_max, int nc, float* y,
                      void* stream);
 
+/* Standalone DFL module (block.py:51-69): x dense fp32 (b, 4*reg_max, a) -> y (b, 4, a): softmax over the
+ * reg_max bins of each side, expectation with weights 0..reg_max-1. */
+int yl_dfl(const float* x, float* y, int b, int reg_max, int a, void* stream);
+
 /* ---- NMS ------------------------------------------------------------------------------------------------
  * Replaces ops.non_max_suppression (utils/ops.py:138-273) including torchvision.ops.nms (ops.py:265):
  * candidate filter (strict >), best-class or multi-label expansion, optional class filter, max_nms top-k,

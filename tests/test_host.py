@@ -1,0 +1,125 @@
+"""CPU tests of the host-side logic: model construction from yaml (parameter counts, state_dict keys identical
+to the reference's), config overrides, C-ABI export list, and the loud failure when no GPU is present."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+PARAMS = {"n": 2624080, "s": 9458752, "m": 20114688}  # reference cfg/yolo11.yaml:8-10
+
+
+@pytest.mark.parametrize("scale", ["n", "s", "m"])
+def test_model_matches_reference_structure(golden, scale):
+    from yololite.nn.tasks import DetectionModel
+
+    m = DetectionModel(f"yolo11{scale}.yaml", verbose=False)
+    assert sum(p.numel() for p in m.parameters()) == PARAMS[scale]
+    g = golden(f"model_yolo11{scale}.npz")
+    ref = {str(k): tuple(int(v) for v in s[: int(nd)]) for k, s, nd in zip(g["keys"], g["shapes"], g["ndims"])}
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert mine == ref                                   # same keys, same shapes, same order-independent set
+    assert list(mine) == list(ref)                       # and same registration order
+    assert m.stride.tolist() == [8.0, 16.0, 32.0]
+    assert m.save == [4, 6, 10, 13, 16, 19, 22]
+    assert all(bn.eps == 1e-3 for bn in m.modules() if isinstance(bn, torch.nn.BatchNorm2d))
+
+
+def test_module_signatures_and_attrs():
+    from yololite.nn.modules import C2PSA, C3k2, DFL, SPPF, Attention, Bottleneck, Conv, Detect, DWConv
+
+    c = Conv(16, 32, 3, 2)
+    assert c.conv.stride == (2, 2) and c.conv.padding == (1, 1) and isinstance(c.act, torch.nn.SiLU)
+    assert isinstance(Conv(8, 8, 1, act=False).act, torch.nn.Identity)
+    assert DWConv(64, 64, 3).conv.groups == 64
+    b = Bottleneck(32, 32)
+    assert b.add and b.cv1.conv.out_channels == 16
+    k = C3k2(64, 128, 1, False, 0.25)
+    assert k.c == 32 and k.cv2.conv.in_channels == 96
+    assert type(C3k2(128, 128, 1, True).m[0]).__name__ == "C3k"
+    a = Attention(128, num_heads=2)
+    assert (a.head_dim, a.key_dim, a.qkv.conv.out_channels) == (64, 32, 256) and a.pe.conv.groups == 128
+    assert C2PSA(256, 256).m[0].attn.num_heads == 2
+    assert SPPF(256, 256).cv2.conv.in_channels == 512
+    d = Detect(80, (64, 128, 256))
+    assert (d.no, d.nl, d.reg_max) == (144, 3, 16) and d.cv3[0][0][0].conv.groups == 64
+    assert DFL(16).conv.weight.flatten().tolist() == list(range(16))
+
+
+def test_modules_refuse_cpu():
+    from yololite.nn.modules import Conv
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Conv(8, 8, 1).eval()(torch.zeros(1, 8, 4, 4))
+
+
+def test_get_cfg_overrides():
+    from yololite.cfg import get_cfg
+
+    a = get_cfg(overrides={"conf": 0.1, "iou": 0.5, "max_det": 10, "classes": [0, 1], "epochs": 3})
+    assert (a.conf, a.iou, a.max_det, a.classes) == (0.1, 0.5, 10, [0, 1])
+    with pytest.raises(SyntaxError):
+        get_cfg(overrides={"cnof": 0.1})
+    with pytest.raises(ValueError):
+        get_cfg(overrides={"conf": 1.5})
+    with pytest.raises(TypeError):
+        get_cfg(overrides={"max_det": 1.5})
+
+
+def test_letterbox_matches_reference_geometry():
+    from yololite.data import LetterBox
+
+    im = np.zeros((1080, 1920, 3), np.uint8)
+    out = LetterBox((640, 640), auto=True, stride=32)(image=im)
+    assert out.shape == (384, 640, 3)                     # boats.jpg -> 384x640
+    out = LetterBox((640, 640), auto=False)(image=im)
+    assert out.shape == (640, 640, 3) and out[0, 0, 0] == 114
+
+
+def test_box_helpers():
+    from yololite.utils import ops
+
+    b = torch.tensor([[10.0, 20.0, 4.0, 6.0]])
+    assert ops.xywh2xyxy(b).tolist() == [[8.0, 17.0, 12.0, 23.0]]
+    assert ops.xyxy2xywh(ops.xywh2xyxy(b)).tolist() == b.tolist()
+    boxes = torch.tensor([[100.0, 50.0, 700.0, 400.0]])
+    out = ops.scale_boxes((384, 640), boxes.clone(), (1080, 1920))
+    assert out[0, 2] == 1920.0 and out[0, 0] == 300.0     # gain 1/3, pad (0, 12)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """include/yl11.h vs libyl11.so vs the ctypes prototypes: all three must agree (no compute calls)."""
+    from yololite import _C
+
+    header = (ROOT / "include" / "yl11.h").read_text()
+    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(yl_\w+)\(", header, re.M))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(str(_C.lib_path()))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in yl11.h but not exported"
+    assert declared == set(_C.EXPORTS)
+    assert _C.load().yl_version() == 100
+
+
+def test_no_gpu_fails_loudly():
+    from yololite import _C
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_C.YLError):
+        _C.init(0)
+    rc = _C.load().yl_init(0)
+    assert rc == -5 and b"no CPU path" in _C.load().yl_last_error_string()
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "yolo-lite_b200"
+    for f in pkg.rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f
+    for f in pkg.rglob("*.cu"):
+        assert "oracle/" not in f.read_text().replace("oracle/ ", "")

@@ -1,0 +1,176 @@
+"""GPU parity of the drop-in nn modules and full models against fixtures produced by the reference itself
+(tests/golden, oracle/gen_golden.py) and against the oracle at BASELINE sizes.
+
+Tolerances (bf16 storage, fp32 accumulation) are the north star's: box coordinates <= 0.5 px, class scores
+<= 1e-2 absolute; intermediate feature maps: |d| <= 4e-2 + 2e-2*|ref| (bf16 has 8 mantissa bits)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import model_state_dict
+
+pytestmark = pytest.mark.gpu
+
+BOX_TOL_PX = 0.5
+SCORE_TOL = 1e-2
+
+
+def feat_close(got, ref, tag):
+    np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=2e-2, atol=4e-2, err_msg=tag)
+
+
+def _mk(tag):
+    from yololite.nn.modules import C2PSA, C3k, C3k2, SPPF, Attention, Bottleneck, Conv, DWConv, PSABlock
+
+    return {
+        "conv_k3s2": lambda: Conv(16, 32, 3, 2), "conv_k1": lambda: Conv(48, 64, 1, 1),
+        "conv_k3s1_noact": lambda: Conv(32, 16, 3, 1, act=False), "conv_stem": lambda: Conv(3, 16, 3, 2),
+        "dwconv": lambda: DWConv(64, 64, 3), "bottleneck": lambda: Bottleneck(32, 32, True),
+        "c3k": lambda: C3k(64, 64, 2), "c3k2_plain": lambda: C3k2(64, 128, 1, False, 0.25),
+        "c3k2_c3k": lambda: C3k2(128, 128, 1, True), "sppf": lambda: SPPF(128, 128, 5),
+        "attention": lambda: Attention(128, num_heads=2, attn_ratio=0.5), "psablock": lambda: PSABlock(128, 0.5, 2),
+        "c2psa": lambda: C2PSA(256, 256, 1),
+    }[tag]()
+
+
+MODULE_TAGS = ["conv_k3s2", "conv_k1", "conv_k3s1_noact", "conv_stem", "dwconv", "bottleneck", "c3k", "c3k2_plain",
+               "c3k2_c3k", "sppf", "attention", "psablock", "c2psa"]
+
+
+@pytest.mark.parametrize("tag", MODULE_TAGS)
+def test_module_matches_reference(golden, tag):
+    from oracle.weights import fill_state_dict_
+
+    g = golden("modules.npz")
+    m = fill_state_dict_(_mk(tag)).cuda().eval()
+    x = torch.from_numpy(g[f"{tag}.x"]).cuda()
+    y = m(x)
+    assert y.dtype == torch.float32 and tuple(y.shape) == g[f"{tag}.y"].shape
+    feat_close(y.cpu().numpy(), g[f"{tag}.y"], tag)
+    y2 = m(x)                                            # cached plan replay gives identical results
+    assert torch.equal(y, y2)
+
+
+def test_dfl_and_detect_match_reference(golden):
+    from oracle.weights import fill_state_dict_
+    from yololite.nn.modules import DFL, Detect
+
+    g = golden("modules.npz")
+    d = DFL(16).cuda()
+    np.testing.assert_allclose(d(torch.from_numpy(g["dfl.x"]).cuda()).cpu().numpy(), g["dfl.y"], rtol=1e-5, atol=1e-5)
+    det = Detect(80, (64, 128, 256))
+    det.stride = torch.tensor([8.0, 16.0, 32.0])
+    fill_state_dict_(det).cuda().eval()
+    y, raw = det([torch.from_numpy(g[f"detect.x{i}"]).cuda() for i in range(3)])
+    for i in range(3):
+        assert tuple(raw[i].shape) == g[f"detect.raw{i}"].shape
+        feat_close(raw[i].cpu().numpy(), g[f"detect.raw{i}"], f"raw{i}")
+    y = y.cpu().numpy()
+    assert np.abs(y[:, :4] - g["detect.y"][:, :4]).max() <= BOX_TOL_PX
+    assert np.abs(y[:, 4:] - g["detect.y"][:, 4:]).max() <= SCORE_TOL
+
+
+@pytest.mark.parametrize("scale", ["n", "s", "m"])
+@pytest.mark.parametrize("graph", [True, False])
+def test_model_matches_reference_golden(golden, scale, graph):
+    from yololite.nn.tasks import DetectionModel
+
+    g = golden(f"model_yolo11{scale}.npz")
+    m = DetectionModel(f"yolo11{scale}.yaml", verbose=False)
+    m.use_cuda_graph = graph
+    m.load_state_dict(model_state_dict(g))
+    m = m.cuda().eval()
+    y, raw = m(torch.from_numpy(g["x"]).cuda())
+    assert tuple(y.shape) == g["y"].shape and y.dtype == torch.float32
+    for i in range(3):
+        assert tuple(raw[i].shape) == g[f"raw{i}"].shape
+        feat_close(raw[i].cpu().numpy(), g[f"raw{i}"], f"raw{i}")
+    y = y.cpu().numpy()
+    assert np.abs(y[:, :4] - g["y"][:, :4]).max() <= BOX_TOL_PX
+    assert np.abs(y[:, 4:] - g["y"][:, 4:]).max() <= SCORE_TOL
+
+
+def test_model_640_matches_oracle_and_nms_end_to_end(golden):
+    """BASELINE config 3 shape (yolo11n, 640x640): head output within tolerance of the fp32 oracle; NMS on the
+    GPU's own pre-NMS tensor is bit-exact against the oracle NMS on the same tensor."""
+    from oracle import nms_ref, yolo11_ref
+    from yololite.nn.tasks import DetectionModel
+    from yololite.utils import ops
+
+    g = golden("model_yolo11n.npz")
+    sd = model_state_dict(g)
+    m = DetectionModel("yolo11n.yaml", verbose=False)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.rand(4, 3, 640, 640, generator=torch.Generator().manual_seed(0))
+    yr, _ = yolo11_ref.forward(sd, x)
+    y, _ = m(x.cuda())
+    assert tuple(y.shape) == (4, 84, 8400)
+    yc = y.cpu().numpy()
+    assert np.abs(yc[:, :4] - yr.numpy()[:, :4]).max() <= BOX_TOL_PX
+    assert np.abs(yc[:, 4:] - yr.numpy()[:, 4:]).max() <= SCORE_TOL
+    for kw in (dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)):
+        got = ops.non_max_suppression(y.clone(), **kw)
+        ref = nms_ref.non_max_suppression(yc, **kw)
+        assert [len(a) for a in got] == [len(b) for b in ref]
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a.cpu().numpy(), b)
+
+
+def test_nms_in_place_side_effect_and_list_layout():
+    from yololite.utils import ops
+
+    p = torch.rand(2, 84, 256, device="cuda")
+    p[:, :4] *= 100
+    before = p.clone()
+    out = ops.non_max_suppression(p, 0.5, 0.5)
+    assert isinstance(out, list) and len(out) == 2 and all(o.shape[1] == 6 and o.dtype == torch.float32 for o in out)
+    torch.testing.assert_close(p[:, :4].transpose(1, 2), ops.xywh2xyxy(before[:, :4].transpose(1, 2)))
+    torch.testing.assert_close(p[:, 4:], before[:, 4:])
+    out2 = ops.non_max_suppression((before.clone(), None), 0.5, 0.5, in_place=False)   # tuple input accepted
+    for a, b in zip(out, out2):
+        assert torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        ops.non_max_suppression(before, conf_thres=1.5)
+    empty = ops.non_max_suppression(torch.zeros(1, 84, 64, device="cuda"), 0.25, 0.45)
+    assert empty[0].shape == (0, 6)
+
+
+def test_yololite_predict_tensor_and_numpy(golden):
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    x = torch.rand(2, 3, 640, 640, generator=torch.Generator().manual_seed(1))
+    res = yl.predict(x, conf=0.05, verbose=False)
+    assert len(res) == 2
+    for r in res:
+        b = r.boxes
+        assert b.data.shape[1] == 6 and r.orig_shape == (640, 640)
+        if len(b):
+            assert float(b.conf.min()) > 0.05 and bool((b.conf[:-1] >= b.conf[1:]).all())
+            assert float(b.xyxy.min()) >= 0 and float(b.xyxy.max()) <= 640
+        assert set(r.speed) == {"preprocess", "inference", "postprocess"}
+    # numpy HWC BGR image, letterboxed 1080x1920 -> 384x640 like the reference predictor
+    im = (np.random.default_rng(0).uniform(0, 255, (1080, 1920, 3))).astype(np.uint8)
+    r2 = yl(im, conf=0.05, verbose=False)
+    assert len(r2) == 1 and r2[0].orig_shape == (1080, 1920)
+    if len(r2[0].boxes):
+        assert float(r2[0].boxes.xyxy[:, [0, 2]].max()) <= 1920 and float(r2[0].boxes.xyxy[:, [1, 3]].max()) <= 1080
+
+
+def test_checkpoint_roundtrip_pt(tmp_path, golden):
+    """A reference-format checkpoint ({'model': module}) loads through YOLOLite('x.pt') and predicts identically."""
+    from yololite import YOLOLite
+    from yololite.nn.tasks import DetectionModel
+
+    g = golden("model_yolo11n.npz")
+    m = DetectionModel("yolo11n.yaml", verbose=False)
+    m.load_state_dict(model_state_dict(g))
+    p = tmp_path / "tiny.pt"
+    torch.save({"model": m.half(), "train_args": {}}, p)
+    yl = YOLOLite(str(p))
+    x = torch.from_numpy(g["x"])
+    y, _ = yl.model.cuda().eval()(x.cuda())
+    assert np.abs(y.cpu().numpy()[:, 4:] - g["y"][:, 4:]).max() <= SCORE_TOL

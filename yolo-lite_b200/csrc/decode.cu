@@ -90,7 +90,34 @@ __global__ void __launch_bounds__(256) detect_decode_kernel(const DecodeParams p
     }
 }
 
+// Standalone DFL (block.py:51-69): x (b, 4*reg_max, a) fp32 channel-major -> (b, 4, a).
+__global__ void __launch_bounds__(256) dfl_kernel(const float* __restrict__ x, float* __restrict__ y, int reg_max,
+                                                  int a, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ai = (int)(i % a);
+    const long long bs = i / a;  // b * 4 + side
+    const float* l = x + bs * reg_max * a + ai;
+    float m = l[0];
+    for (int k = 1; k < reg_max; ++k) m = fmaxf(m, l[(long long)k * a]);
+    float s = 0.f, e = 0.f;
+    for (int k = 0; k < reg_max; ++k) {
+        const float w = expf(l[(long long)k * a] - m);
+        s += w;
+        e += w * (float)k;
+    }
+    y[i] = e / s;
+}
+
 }  // namespace yl
+
+extern "C" int yl_dfl(const float* x, float* y, int b, int reg_max, int a, void* stream) {
+    YL_CHECK(x && y && b > 0 && reg_max > 0 && a > 0, YL_ERR_ARG, "bad arguments");
+    const long long total = (long long)b * 4 * a;
+    yl::dfl_kernel<<<(unsigned)yl::ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, reg_max, a, total);
+    YL_LAUNCH_OK("dfl_kernel");
+    return YL_OK;
+}
 
 extern "C" int yl_detect_decode(const yl_tensor* levels, int nl, const float* strides_host, int reg_max, int nc,
                                 float* y, void* stream) {

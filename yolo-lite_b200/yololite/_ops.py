@@ -168,6 +168,16 @@ def detect_decode(levels: list[View], strides, reg_max: int, nc: int, y: torch.T
              "yl_detect_decode")
 
 
+def dfl_expectation(x: torch.Tensor, reg_max: int) -> torch.Tensor:
+    lib = _C.init(x.device)
+    b, c, a = x.shape
+    assert c == 4 * reg_max
+    x = x.contiguous().float()
+    y = torch.empty((b, 4, a), dtype=torch.float32, device=x.device)
+    _C.check(lib.yl_dfl(x.data_ptr(), y.data_ptr(), b, reg_max, a, _C.stream_ptr()), "yl_dfl")
+    return y
+
+
 class NmsWorkspace:
     """Grow-only device scratch for yl_nms_batched, cached per device."""
 

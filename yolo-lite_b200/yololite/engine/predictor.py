@@ -1,0 +1,152 @@
+"""DetectionPredictor (reference yololite/engine/predictor.py:21-323): preprocess -> inference -> postprocess
+per batch, yielding `Results`.  The three stages keep the reference's names and the `speed` dict; what changed:
+
+  * inference is one CUDA-graph replay of the model plan (reference: ~300 ATen launches);
+  * postprocess keeps detections on the device: batched NMS + box rescale/clip kernels, one host read of the
+    counts, and no device->host copy of the input batch for tensor sources unless a caller asks for
+    `orig_img` (the reference always converts the whole batch to uint8 numpy, ops.py:487-488);
+  * saving / plotting / video writing (predictor.py:248-323) are I/O features outside the hot path.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch
+
+from .. import _C
+from ..cfg import DEFAULT_CFG, get_cfg
+from ..data import LetterBox, load_inference_source
+from ..nn.autobackend import AutoBackend
+from ..utils import LOGGER, ops
+from ..utils.torch_utils import select_device, smart_inference_mode
+from .results import Results
+
+
+class _LazyTensorImage:
+    """orig_img stand-in for tensor sources: converts to HWC uint8 numpy only when somebody looks at it."""
+
+    def __init__(self, batch: torch.Tensor, i: int):
+        self._b, self._i = batch, i
+        self.shape = (batch.shape[2], batch.shape[3], batch.shape[1])
+
+    def __array__(self, dtype=None, copy=None):
+        a = (self._b[self._i].permute(1, 2, 0) * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class DetectionPredictor:
+    def __init__(self, cfg=DEFAULT_CFG, overrides=None):
+        self.args = get_cfg(cfg, overrides)
+        if self.args.conf is None:
+            self.args.conf = 0.25
+        if self.args.save or self.args.save_txt or self.args.save_crop or self.args.show:
+            if self.args.verbose:
+                LOGGER.info("save/show requested: result files and plots are outside yololite's scope; ignored")
+        self.done_warmup = False
+        self.model = None
+        self.data = self.args.data
+        self.imgsz = None
+        self.device = None
+        self.dataset = None
+        self.batch = None
+        self.results = None
+        self.seen = 0
+        self.source_type = None
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ stages
+    def pre_transform(self, im):
+        same_shapes = len({x.shape for x in im}) == 1
+        letterbox = LetterBox(self.imgsz, auto=same_shapes and self.model.pt, stride=self.model.stride)
+        return [letterbox(image=x) for x in im]
+
+    def preprocess(self, im):
+        """BCHW float tensor: `.to(device).float()`.  list of HWC BGR uint8: letterbox, BGR->RGB, /255."""
+        if isinstance(im, torch.Tensor):
+            return im.to(self.device, non_blocking=True).float()
+        arr = np.stack(self.pre_transform(im))
+        arr = np.ascontiguousarray(arr[..., ::-1].transpose((0, 3, 1, 2)))
+        t = torch.from_numpy(arr).to(self.device, non_blocking=True).float()
+        t /= 255
+        return t
+
+    def inference(self, im, *args, **kwargs):
+        return self.model(im)
+
+    def postprocess(self, preds, img, orig_imgs):
+        a = self.args
+        dets, counts = ops.nms_padded(preds, a.conf, a.iou, a.classes, a.agnostic_nms, False, a.max_det)
+        B = dets.shape[0]
+        tensor_src = isinstance(orig_imgs, torch.Tensor)
+        shapes = [tuple(orig_imgs.shape[2:])] * B if tensor_src else [im.shape[:2] for im in orig_imgs]
+        params = np.empty((B, 5), np.float32)
+        for i, s0 in enumerate(shapes):
+            gain, pad = ops.letterbox_params(tuple(img.shape[2:]), s0)
+            params[i] = (gain, pad[0], pad[1], s0[1], s0[0])
+        pd = torch.from_numpy(params).to(dets.device, non_blocking=True)
+        _C.check(_C.load().yl_scale_boxes(dets.data_ptr(), counts.data_ptr(), B, dets.shape[1], pd.data_ptr(),
+                                          _C.stream_ptr()), "yl_scale_boxes")
+        n = counts.tolist()  # single host sync
+        dets = dets.clone()  # results must not alias the NMS output buffer of the next batch
+        results = []
+        for i in range(B):
+            orig = _LazyTensorImage(orig_imgs, i) if tensor_src else orig_imgs[i]
+            r = Results(orig, path=self.batch[0][i], names=self.model.names, boxes=dets[i, : n[i]])
+            results.append(r)
+        return results
+
+    # ------------------------------------------------------------------ driver
+    def __call__(self, source=None, model=None, stream=False, *args, **kwargs):
+        self.stream = stream
+        gen = self.stream_inference(source, model, *args, **kwargs)
+        return gen if stream else list(gen)
+
+    def setup_source(self, source):
+        s = self.args.imgsz
+        s = [s, s] if isinstance(s, int) else list(s)
+        stride = self.model.stride
+        self.imgsz = [max(int(np.ceil(v / stride) * stride), stride) for v in s]
+        self.dataset = load_inference_source(source=source, batch=self.args.batch, vid_stride=self.args.vid_stride,
+                                             buffer=self.args.stream_buffer)
+        self.source_type = self.dataset.source_type
+
+    @smart_inference_mode()
+    def stream_inference(self, source=None, model=None, *args, **kwargs):
+        if not self.model:
+            self.setup_model(model)
+        with self._lock:
+            self.setup_source(source if source is not None else self.args.source)
+            self.seen, self.batch = 0, None
+            profilers = tuple(ops.Profile(device=self.device) for _ in range(3))
+            for self.batch in self.dataset:
+                paths, im0s, s = self.batch
+                with profilers[0]:
+                    im = self.preprocess(im0s)
+                with profilers[1]:
+                    preds = self.inference(im, *args, **kwargs)
+                with profilers[2]:
+                    self.results = self.postprocess(preds, im, im0s)
+                n = len(self.results)
+                for i in range(n):
+                    self.seen += 1
+                    self.results[i].speed = {
+                        "preprocess": profilers[0].dt * 1e3 / n,
+                        "inference": profilers[1].dt * 1e3 / n,
+                        "postprocess": profilers[2].dt * 1e3 / n,
+                    }
+                    if self.args.verbose:
+                        LOGGER.info(f"{s[i]}{im.shape[2]}x{im.shape[3]} {self.results[i].verbose()}"
+                                    f"{profilers[1].dt * 1e3 / n:.2f}ms")
+                yield from self.results
+        if self.args.verbose and self.seen:
+            t = tuple(x.t / self.seen * 1e3 for x in profilers)
+            LOGGER.info("Speed: %.2fms preprocess, %.2fms inference, %.2fms postprocess per image" % t)
+
+    def setup_model(self, model, verbose=True):
+        self.model = AutoBackend(weights=model or self.args.model, device=select_device(self.args.device),
+                                 dnn=self.args.dnn, data=self.args.data, fp16=self.args.half, batch=self.args.batch,
+                                 fuse=True, verbose=verbose and self.args.verbose)
+        self.device = self.model.device
+        self.args.half = self.model.fp16
+        self.model.eval()

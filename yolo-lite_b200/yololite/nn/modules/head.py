@@ -1,0 +1,95 @@
+"""Detect head of YOLO11 (reference yololite/nn/modules/head.py:16-168, non-end2end path).
+
+Same constructor, attributes (`nc, nl, reg_max, no, stride, cv2, cv3, dfl`), class attributes and state_dict
+keys as the reference.  Per level the box branch (Conv3x3, Conv3x3, Conv2d1x1) and the class branch
+(DW3x3+Conv1x1, DW3x3+Conv1x1, Conv2d1x1; `legacy` = three dense convs) write their last 1x1 conv in fp32
+into the two channel slices of one (B, H, W, 4*reg_max + nc) raw map — the reference's per-level `torch.cat`
+(head.py:64-65) — and a single decode kernel turns the three raw maps into the (B, 4+nc, A) prediction
+(`_inference`, head.py:95-126).
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import torch
+import torch.nn as nn
+
+from ._emit import YLModule, emit_any
+from .block import DFL
+from .conv import Conv, DWConv
+
+__all__ = ("Detect",)
+
+
+class Detect(YLModule):
+    dynamic = False
+    export = False
+    format = None
+    end2end = False
+    max_det = 300
+    shape = None
+    anchors = torch.empty(0)
+    strides = torch.empty(0)
+    legacy = False
+
+    def __init__(self, nc=80, ch=()):
+        super().__init__()
+        self.nc = nc
+        self.nl = len(ch)
+        self.reg_max = 16
+        self.no = nc + self.reg_max * 4
+        self.stride = torch.zeros(self.nl)
+        c2, c3 = max((16, ch[0] // 4, self.reg_max * 4)), max(ch[0], min(self.nc, 100))
+        self.cv2 = nn.ModuleList(
+            nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), nn.Conv2d(c2, 4 * self.reg_max, 1)) for x in ch
+        )
+        if self.legacy:
+            self.cv3 = nn.ModuleList(
+                nn.Sequential(Conv(x, c3, 3), Conv(c3, c3, 3), nn.Conv2d(c3, self.nc, 1)) for x in ch
+            )
+        else:
+            self.cv3 = nn.ModuleList(
+                nn.Sequential(
+                    nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1)),
+                    nn.Sequential(DWConv(c3, c3, 3), Conv(c3, c3, 1)),
+                    nn.Conv2d(c3, self.nc, 1),
+                )
+                for x in ch
+            )
+        self.dfl = DFL(self.reg_max) if self.reg_max > 1 else nn.Identity()
+        if self.end2end:
+            raise NotImplementedError("end2end (YOLOv10-style) heads are not part of the YOLO11 path")
+
+    # ------------------------------------------------------------------ plan
+    def _emit(self, g, feats, out=None):
+        """feats: list of nl NHWC views. Returns (y tensor (B, 4+nc, A) fp32, [raw NHWC f32 views])."""
+        assert len(feats) == self.nl
+        if float(self.stride.sum()) == 0.0:
+            raise RuntimeError("Detect.stride is unset (it is filled in by DetectionModel)")
+        nbox = 4 * self.reg_max
+        raws = []
+        for i, x in enumerate(feats):
+            raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32)
+            emit_any(g, self.cv2[i], x, out=raw.slice(0, nbox), out_dtype=torch.float32)
+            emit_any(g, self.cv3[i], x, out=raw.slice(nbox, self.nc), out_dtype=torch.float32)
+            raws.append(raw)
+        y = g.detect_decode(raws, [float(s) for s in self.stride], self.reg_max, self.nc)
+        return y, raws
+
+    def _yl_export(self, g, res):
+        y, raws = res
+        return y, [g.to_nchw(r) for r in raws]
+
+    def forward(self, x):
+        """list of nl NCHW feature maps -> (y, [raw maps (B, no, H, W)]) like the reference in eval mode."""
+        if self.training:
+            raise NotImplementedError("yololite is inference-only: call .eval() (training is out of scope)")
+        return super().forward(list(x))
+
+    def bias_init(self):
+        """Reference head.py:128-139: box bias 1.0, class bias log(5 / nc / (640 / s)^2)."""
+        for a, b, s in zip(self.cv2, self.cv3, self.stride):
+            a[-1].bias.data[:] = 1.0
+            b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / float(s)) ** 2)
+        self._yl_invalidate()
