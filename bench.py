@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — YOLO11 inference hot path on B200: preprocessed tensor in -> NMS'd detections out.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model n|s|m] [--batch B]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       (one rank per GPU, weak scaling)
+
+One "step" = one pass of the hot path over one batch of synthetic 640x640 images (BASELINE.json config 3:
+yolo11n, bs=64 per GPU, bf16 storage / fp32 accumulate): image ingest (NCHW fp32 -> NHWC bf16), the whole
+model as one CUDA-graph replay of this repo's sm_100a kernels, DFL/anchor decode, and batched NMS
+(conf=0.25, iou=0.7, max_det=300: the predictor defaults).  Rank 0 prints ONE JSON line.
+
+  value      images/s, inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks
+  e2e        images/s through the public API (YOLOLite.predict) from a pinned HOST tensor, H2D + D2H inside
+  roofline   dominant kernel (conv_tc_kernel, all its launches of a step): algorithmic bytes / measured time
+             vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port of the reference's CPU path (oracle/yolo11_ref.py + oracle/nms_ref.py) timed
+             on this box's host cores on a bounded sample
+
+`--impl reference` times that same CPU path alone (the reference is pure Python/ATen, there is nothing to
+compile into oracle/_ref; /root/reference does not exist on the GPU box, so the oracle port stands in).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT / "yolo-lite_b200"), str(ROOT)]
+
+CONF, IOU, MAX_DET = 0.25, 0.7, 300
+IMG = 640
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="n", choices=["n", "s", "m"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ synthetic
+def randomise_model_(model, seed=1):
+    """BN gamma~U(.5,1.5), beta,mean~N(0,.1), var~U(.5,1.5); Detect class bias ~N(-4,1.5) so
+    scores spread over (0,1) (default bias_init gives ~1e-5 and zero candidates)."""
+    g = torch.Generator().manual_seed(seed)
+    for name, m in model.named_modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+    det = model.model[-1]
+    for seq in det.cv3:
+        seq[-1].bias.data.copy_(torch.randn(seq[-1].bias.shape, generator=g) * 1.5 - 4.0)
+    return model
+
+
+def synth_images(batch, n_sets, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(batch, 3, IMG, IMG, generator=g) for _ in range(n_sets)]
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU path
+def cpu_reference_step(sd, x):
+    """The reference's CPU hot path restated: unfused fp32 forward + non_max_suppression (oracle port)."""
+    from oracle import nms_ref, yolo11_ref
+
+    y, _ = yolo11_ref.forward(sd, x)
+    return nms_ref.non_max_suppression(y.numpy(), conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
+
+
+def time_cpu(model_sd, batch, reps, warm=1):
+    x = synth_images(batch, 1, seed=0)[0]
+    for _ in range(warm):
+        cpu_reference_step(model_sd, x)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(model_sd, x)
+        ts.append(time.perf_counter() - t0)
+    return batch / statistics.median(ts), ts
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    model_name = f"yolo11{a.model}"
+    workload = f"{model_name} synthetic {IMG}x{IMG} bs={a.batch}/GPU, predict NMS conf={CONF} iou={IOU} max_det={MAX_DET}"
+
+    from yololite.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    model = randomise_model_(DetectionModel(f"{model_name}.yaml", verbose=False)).eval()
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        threads = max(1, min(os.cpu_count() or 1, 64))
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        sample_b = 8
+        t_probe0 = time.perf_counter()
+        cpu_reference_step(sd, synth_images(sample_b, 1)[0])
+        probe = time.perf_counter() - t_probe0
+        budget = 150.0                                      # keep the whole arm within a few minutes
+        steps = max(1, min(a.steps, int(budget / max(probe, 1e-3)) - a.warmup))
+        warm = min(a.warmup, max(0, int(20.0 / max(probe, 1e-3))))
+        v, ts = time_cpu(sd, sample_b, steps, warm)
+        line = {
+            "impl": "reference", "metric": "images_per_sec", "value": round(v, 3), "unit": "images/s",
+            "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(statistics.median(ts) * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": f"{sample_b} images/step of the bs={a.batch} workload"},
+            "cpu_baseline": {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle port (yolo11_ref fp32 unfused + nms_ref), {sample_b}-image steps x{steps}"},
+            "e2e": {"value": round(v, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- ours
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from yololite import _C
+    from yololite.utils import ops
+
+    _C.init(dev)
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(dev)
+    n_sets = 3                                              # rotate inputs: 3 x 315 MB >> 126 MB L2
+    host = [t.pin_memory() for t in synth_images(a.batch, n_sets, seed=rank)]
+    devx = [t.to(dev) for t in host]
+
+    def step(x):
+        y, _ = model.infer(x)
+        return ops.nms_padded(y, CONF, IOU, None, False, False, MAX_DET)
+
+    for i in range(max(a.warmup, 3)):
+        dets, counts = step(devx[i % n_sets])
+    torch.cuda.synchronize(dev)
+    plan = model._get_plan(devx[0].shape, dev)[0]
+    launches_per_step = plan.n_launches + 2                 # + nms_filter + nms_select
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region: K steps, CUDA events on the launching (current) stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            dets, counts = step(devx[i % n_sets])
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    n_det_local = int(counts.sum().item())
+
+    # ---- e2e through the public API, host tensors, H2D + D2H inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        from yololite import YOLOLite
+
+        yl = YOLOLite(f"{model_name}.yaml")
+        yl.model.load_state_dict(sd_cpu)
+        yl.model.to(dev)
+        kw = dict(conf=CONF, iou=IOU, max_det=MAX_DET, verbose=False, device=dev, batch=a.batch)
+        for i in range(3):
+            yl.predict(host[i % n_sets], **kw)
+        steps_e = max(3, min(a.steps, 20))
+        barrier()
+        t0 = time.perf_counter()
+        nd = 0
+        for i in range(steps_e):
+            res = yl.predict(host[i % n_sets], **kw)
+            for r in res[:1]:
+                nd += len(r.boxes.data.cpu())               # device->host read of a result
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(a.batch * world * steps_e / float(te.item()), 1), "unit": "images/s",
+               "h2d_bytes_per_step": a.batch * 3 * IMG * IMG * 4, "d2h_bytes_per_step": a.batch * 4 + MAX_DET * 6 * 4,
+               "steps": steps_e, "api": "YOLOLite.predict(pinned host fp32 BCHW tensor)"}
+
+    # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager pass
+    roof, breakdown = None, None
+    if rank == 0:
+        model.infer(devx[0])
+        torch.cuda.synchronize(dev)
+        lt = plan.time_launches(reps=3)
+        kinds = {}
+        for m_, t_ in zip(plan.meta, lt):
+            k = kinds.setdefault(m_["kind"], {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+            k["ms"] += t_
+            k["bytes"] += m_["bytes"]
+            k["flops"] += m_["flops"]
+            k["launches"] += 1
+        total_ms = sum(k["ms"] for k in kinds.values())
+        breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 3), "launches": v["launches"],
+                         "GB": round(v["bytes"] / 1e9, 4), "GFLOP": round(v["flops"] / 1e9, 2)}
+                     for k, v in sorted(kinds.items(), key=lambda kv: -kv[1]["ms"])}
+        hbm, tf, src = peaks()
+        top = max(kinds.items(), key=lambda kv: kv[1]["ms"])[0]
+        tk = kinds[top]
+        ach = tk["bytes"] / 1e9 / (tk["ms"] / 1e3)
+        roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(ach / hbm, 4), "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({src})",
+                "launches_per_step": tk["launches"], "avg_launch_us": round(tk["ms"] * 1e3 / tk["launches"], 2),
+                "tensor_tflops": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3), 1), "tensor_peak_tflops": tf,
+                "tensor_frac": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3) / tf, 4)}
+
+    # ---- detections gathered for the metric only (no collective on the hot path)
+    n_det = n_det_local
+    if dist is not None:
+        tt = torch.tensor([n_det_local], device=dev)
+        dist.all_reduce(tt)
+        n_det = int(tt.item())
+
+    cpu_b = None
+    if rank == 0 and not a.no_cpu_baseline:
+        threads = max(1, min(os.cpu_count() or 1, 64))
+        torch.set_num_threads(threads)
+        v, ts = time_cpu(sd_cpu, 8, reps=3, warm=1)
+        cpu_b = {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": "port",
+                 "sample": f"oracle port (yolo11_ref fp32 unfused + nms_ref), 8 of {a.batch} images x3 reps, "
+                           f"{sum(ts):.1f}s CPU wall"}
+
+    if rank == 0:
+        total_images = a.batch * world * a.steps
+        line = {
+            "metric": "images_per_sec", "value": round(total_images / (ms_max / 1e3), 1), "unit": "images/s",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_max / a.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": a.batch * world, "parallelism": f"dp{world} batch-sharded, no collective",
+                       "l2": f"{n_sets} rotating input batches of {a.batch * 3 * IMG * IMG * 4 / 1e6:.0f} MB each (> L2)",
+                       "weights": "random init from cfg/yolo11.yaml, BN statistics randomised (seed 1)"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+            "launches_per_step": launches_per_step, "detections_last_step": n_det,
+            "roofline": roof, "cpu_baseline": cpu_b, "kernel_breakdown": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

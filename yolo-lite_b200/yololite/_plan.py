@@ -36,6 +36,7 @@ class Builder:
         self.calls: list[tuple] = []      # (fn, args tuple without stream, keepalive)
         self.buffers: list[torch.Tensor] = []
         self.bytes = 0
+        self.meta: list[dict] = []
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -52,15 +53,18 @@ class Builder:
         assert (out.n, out.h, out.w, out.c) == (n, h, w, c), ((out.n, out.h, out.w, out.c), (n, h, w, c))
         return out
 
-    def _push(self, fn, *args, keep=()):
+    def _push(self, fn, *args, keep=(), kind="", bytes_=0, flops=0):
         self.calls.append((fn, args, keep))
+        # algorithmic work of the launch (each operand touched once): the roofline numerators of DESIGN.md
+        self.meta.append({"kind": kind or fn.__name__, "bytes": int(bytes_), "flops": int(flops)})
 
     # ------------------------------------------------------------------ ops
     def input_nchw(self, x_nchw_static: torch.Tensor) -> View:
         n, c, h, w = x_nchw_static.shape
         v = self.alloc(n, h, w, c)
         t = v.ct()
-        self._push(self.lib.yl_nchw_to_nhwc, x_nchw_static.data_ptr(), C.byref(t), keep=(t, x_nchw_static))
+        self._push(self.lib.yl_nchw_to_nhwc, x_nchw_static.data_ptr(), C.byref(t), keep=(t, x_nchw_static),
+                   kind="ingest_nchw_to_nhwc", bytes_=n * c * h * w * (4 + 2))
         return v
 
     def conv(self, x: View, pc: PackedConv, stride=1, act=True, out=None, res: View | None = None,
@@ -74,34 +78,47 @@ class Builder:
             assert stride == 1 and k == 3 and not upsample
             xt, yt = x.ct(), y.ct()
             rt = res.ct() if res is not None else None
+            px = x.n * x.h * x.w
             self._push(self.lib.yl_dwconv3x3, C.byref(xt), C.byref(yt), pc.w.data_ptr(), pc.bias.data_ptr(), int(act),
-                       C.byref(rt) if rt is not None else None, keep=(xt, yt, rt, pc))
+                       C.byref(rt) if rt is not None else None, keep=(xt, yt, rt, pc), kind="dwconv3x3",
+                       bytes_=px * x.c * 2 * (2 + (res is not None)) + 9 * x.c * 2, flops=2 * 9 * px * x.c)
             return y
         a = _ops.conv_args(x, y, pc, stride, act, res, upsample, impl)
-        self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc))
+        opx = x.n * ho * wo
+        esz = 4 if out_dtype is torch.float32 else 2
+        tc = impl != _C.IMPL_DIRECT and bool(self.lib.yl_conv_tc_supported(C.byref(a)))
+        self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc), kind="conv_tc" if tc else "conv_direct",
+                   bytes_=x.n * x.h * x.w * x.c * 2 + opx * pc.co * esz * u * u + k * k * x.c * pc.co * 2
+                   + (opx * pc.co * 2 if res is not None else 0),
+                   flops=2 * opx * pc.co * x.c * k * k)
         return y
 
     def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):
         ts = [v.ct() for v in (x, y1, y2, y3)]
-        self._push(self.lib.yl_sppf_pool, *[C.byref(t) for t in ts], k, keep=tuple(ts))
+        self._push(self.lib.yl_sppf_pool, *[C.byref(t) for t in ts], k, keep=tuple(ts), kind="sppf_pool",
+                   bytes_=x.n * x.h * x.w * x.c * 2 * 4)
 
     def upsample2x(self, x: View, out=None) -> View:
         y = self._out(out, x.n, 2 * x.h, 2 * x.w, x.c)
         xt, yt = x.ct(), y.ct()
-        self._push(self.lib.yl_upsample2x, C.byref(xt), C.byref(yt), keep=(xt, yt))
+        self._push(self.lib.yl_upsample2x, C.byref(xt), C.byref(yt), keep=(xt, yt), kind="upsample2x",
+                   bytes_=x.n * x.h * x.w * x.c * 2 * 5)
         return y
 
     def copy(self, x: View, out=None) -> View:
         y = self._out(out, x.n, x.h, x.w, x.c)
         xt, yt = x.ct(), y.ct()
-        self._push(self.lib.yl_copy_slice, C.byref(xt), C.byref(yt), keep=(xt, yt))
+        self._push(self.lib.yl_copy_slice, C.byref(xt), C.byref(yt), keep=(xt, yt), kind="copy_slice",
+                   bytes_=x.n * x.h * x.w * x.c * 2 * 2)
         return y
 
     def attention(self, qkv: View, heads: int, key_dim: int, head_dim: int, scale: float, out=None) -> View:
         y = self._out(out, qkv.n, qkv.h, qkv.w, heads * head_dim)
         qt, yt = qkv.ct(), y.ct()
+        ntok = qkv.h * qkv.w
         self._push(self.lib.yl_psa_attention, C.byref(qt), C.byref(yt), heads, key_dim, head_dim, float(scale),
-                   keep=(qt, yt))
+                   keep=(qt, yt), kind="psa_attention", bytes_=qkv.n * ntok * (qkv.c + heads * head_dim) * 2,
+                   flops=2 * qkv.n * heads * ntok * ntok * (key_dim + head_dim))
         return y
 
     def detect_decode(self, levels: list[View], strides, reg_max: int, nc: int) -> torch.Tensor:
@@ -111,14 +128,16 @@ class Builder:
         self.buffers.append(y)
         arr = (_C.Tensor * len(levels))(*[v.ct() for v in levels])
         st = (C.c_float * len(levels))(*[float(s) for s in strides])
-        self._push(self.lib.yl_detect_decode, arr, len(levels), st, reg_max, nc, y.data_ptr(), keep=(arr, st))
+        self._push(self.lib.yl_detect_decode, arr, len(levels), st, reg_max, nc, y.data_ptr(), keep=(arr, st),
+                   kind="detect_decode", bytes_=n * a * ((4 * reg_max + nc) * 4 + (4 + nc) * 4))
         return y
 
     def to_nchw(self, x: View) -> torch.Tensor:
         out = torch.empty((x.n, x.c, x.h, x.w), dtype=torch.float32, device=self.device)
         self.buffers.append(out)
         xt = x.ct()
-        self._push(self.lib.yl_nhwc_to_nchw, C.byref(xt), out.data_ptr(), keep=(xt,))
+        self._push(self.lib.yl_nhwc_to_nchw, C.byref(xt), out.data_ptr(), keep=(xt,), kind="export_nhwc_to_nchw",
+                   bytes_=x.n * x.h * x.w * x.c * (x.buf.element_size() + 4))
         return out
 
     def finish(self) -> "Plan":
@@ -131,16 +150,27 @@ class Plan:
     def __init__(self, b: Builder):
         self.device = b.device
         self.calls = b.calls
+        self.meta = b.meta
         self.buffers = b.buffers
         self.bytes = b.bytes
         self.graph: torch.cuda.CUDAGraph | None = None
+        self._skip = 0
         self.n_launches = len(b.calls)
 
-    def run(self):
+    def run(self, ingest_ptr: int | None = None):
+        """Replay.  `ingest_ptr`: device pointer of an NCHW fp32 batch to read instead of the static input
+        (only the first call, the image ingest, consumes it; it is never part of the CUDA graph)."""
+        s = _C.stream_ptr()
+        first = 0
+        if self.graph is not None or ingest_ptr is not None:
+            for fn, args, _ in self.calls[: self._skip if self.graph is not None else 1]:
+                a = (ingest_ptr,) + tuple(args[1:]) if (ingest_ptr is not None and fn.__name__ == "yl_nchw_to_nhwc") else args
+                _C.check(fn(*a, s), fn.__name__)
+            first = self._skip if self.graph is not None else 1
         if self.graph is not None:
             self.graph.replay()
             return
-        self.run_eager()
+        self.run_eager(first)
 
     def run_eager(self, skip: int = 0):
         s = _C.stream_ptr()
@@ -149,6 +179,23 @@ class Plan:
             rc = fn(*args, s)
             if rc != 0:
                 check(rc, fn.__name__)
+
+    def time_launches(self, reps: int = 3):
+        """Per-launch device time (ms, median of `reps` eager passes in plan order) via CUDA events on the
+        launching stream.  Cache state is the real one: each launch runs right after its producers."""
+        n = len(self.calls)
+        s = _C.stream_ptr()
+        times = []
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            ev[0].record()
+            for i, (fn, args, _) in enumerate(self.calls):
+                _C.check(fn(*args, s), fn.__name__)
+                ev[i + 1].record()
+            torch.cuda.synchronize(self.device)
+            times.append([ev[i].elapsed_time(ev[i + 1]) for i in range(n)])
+        t = torch.tensor(times).median(0).values.tolist()
+        return t
 
     def capture(self, skip: int = 0):
         """Capture calls[skip:] into a CUDA graph (calls[:skip] stay eager, e.g. the image ingest)."""
@@ -160,14 +207,4 @@ class Plan:
             self.run_eager(skip)
         self.graph = g
         self._skip = skip
-        if skip:
-            eager = self.calls[:skip]
-
-            def run():
-                s = _C.stream_ptr()
-                for fn, args, _ in eager:
-                    _C.check(fn(*args, s), fn.__name__)
-                g.replay()
-
-            self.run = run  # type: ignore[method-assign]
         return self

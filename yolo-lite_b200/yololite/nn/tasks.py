@@ -272,7 +272,7 @@ class BaseModel(YLModule):
                 y, raws = self._emit(g, xin)
                 plan = g.finish()
                 if self.use_cuda_graph:
-                    plan.capture()
+                    plan.capture(skip=1)     # the image ingest stays eager so it can read the caller's tensor
                 raw_views = [r.buf.permute(0, 3, 1, 2) for r in raws]   # (B, no, H, W) views, zero-copy
                 entry = (plan, static_in, y, raw_views)
             plans[key] = entry
@@ -298,8 +298,11 @@ class BaseModel(YLModule):
             raise ValueError(f"image size {tuple(x.shape[2:])} must be a multiple of the model stride {s}")
         plan, static_in, y, raws = self._get_plan(x.shape, dev)
         with torch.cuda.device(dev):
-            static_in.copy_(x, non_blocking=True)
-            plan.run()
+            if x.dtype == torch.float32 and x.is_contiguous():
+                plan.run(ingest_ptr=x.data_ptr())          # zero-copy: the ingest kernel reads x directly
+            else:
+                static_in.copy_(x, non_blocking=True)
+                plan.run()
         return y, raws
 
     def fuse(self, verbose=True):
