@@ -100,6 +100,12 @@ int yl_conv_bn_act(const yl_conv_args* a, void* stream);
 /* 1 if the tcgen05 implicit-GEMM path can run this problem, 0 if it needs the direct kernel. */
 int yl_conv_tc_supported(const yl_conv_args* a);
 
+/* First layer fused with the image ingest (predictor.py:81-84 + conv.py:35-53): reads the NCHW fp32 batch
+ * (values rounded to bf16 like every other activation), 3x3 stride-2 pad-1 conv, <= 4 input channels, folded
+ * BN + SiLU, NHWC bf16 out.  y->c in {16, 32, 48, 64, 96}. */
+int yl_stem_conv(const float* x_nchw, int n, int ci, int h, int w, const void* w_packed, int ci_pad,
+                 const float* bias, const yl_tensor* y, int act, void* stream);
+
 /* DWConv (conv.py:100-105), depthwise 3x3 stride 1 pad 1 + folded BN (+SiLU): head.py:46-47, block.py:893.
  * w is bf16 [9][c]; optional residual-style `add` tensor is summed after activation (Attention: + pe(v)). */
 int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const float* bias, int act,

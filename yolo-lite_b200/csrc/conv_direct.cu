@@ -305,3 +305,100 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ fused stem
+// First layer of the network fused with the image ingest: reads the caller's NCHW fp32 batch directly
+// (predictor.py:81-84 `.to(device).float()`), 3x3 stride-2 conv with <= 4 input channels, folded BN, SiLU,
+// writes NHWC bf16.  Replaces a layout pass (read 4.9 MB + write 2.5 MB per image) plus a conv pass with one
+// kernel whose traffic is the algorithmic minimum (read image once, write activations once).
+// One thread = one output pixel x CO channels; weights are staged in shared memory as fp32 [tap][ci][CO] and
+// read as warp-uniform 16-byte broadcasts.
+namespace yl {
+
+template <int CO>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int N, int Ci, int H, int W,
+                                                        const __nv_bfloat16* __restrict__ wp, int ci_pad,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                        long long y_cstride, int y_coff, int Ho, int Wo, int act) {
+    __shared__ __align__(16) float sw[9 * 4 * CO];
+    __shared__ float sb[CO];
+    for (int i = threadIdx.x + threadIdx.y * 32; i < 9 * 4 * CO; i += 256) {
+        const int co = i % CO, ci = (i / CO) % 4, tap = i / (4 * CO);
+        sw[i] = ci < Ci ? __bfloat162float(wp[(long long)co * 9 * ci_pad + tap * ci_pad + ci]) : 0.f;
+    }
+    for (int i = threadIdx.x + threadIdx.y * 32; i < CO; i += 256) sb[i] = bias[i];
+    __syncthreads();
+    const int wo = blockIdx.x * 32 + threadIdx.x;
+    const int ho = blockIdx.y * 8 + threadIdx.y;
+    const int n = blockIdx.z;
+    if (wo >= Wo || ho >= Ho) return;
+
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = sb[c];
+    const long long plane = (long long)H * W;
+    const float* xn = x + (long long)n * Ci * plane;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int hi = 2 * ho + r - 1;
+        if (hi < 0 || hi >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int wi = 2 * wo + s - 1;
+            if (wi < 0 || wi >= W) continue;
+            for (int ci = 0; ci < Ci; ++ci) {
+                // the model consumes bf16 images: round here exactly like the NHWC bf16 ingest did
+                const float xv = __bfloat162float(__float2bfloat16_rn(__ldg(xn + ci * plane + (long long)hi * W + wi)));
+                const float4* wv = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 4 + ci) * CO);
+#pragma unroll
+                for (int c4 = 0; c4 < CO / 4; ++c4) {
+                    const float4 w4 = wv[c4];
+                    acc[c4 * 4 + 0] = fmaf(xv, w4.x, acc[c4 * 4 + 0]);
+                    acc[c4 * 4 + 1] = fmaf(xv, w4.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(xv, w4.z, acc[c4 * 4 + 2]);
+                    acc[c4 * 4 + 3] = fmaf(xv, w4.w, acc[c4 * 4 + 3]);
+                }
+            }
+        }
+    }
+    __nv_bfloat16* dst = y + (((long long)n * Ho + ho) * Wo + wo) * y_cstride + y_coff;
+#pragma unroll
+    for (int c8 = 0; c8 < CO / 8; ++c8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = act ? silu_f(acc[c8 * 8 + i]) : acc[c8 * 8 + i];
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        reinterpret_cast<uint4*>(dst)[c8] = o;
+    }
+}
+
+}  // namespace yl
+
+extern "C" int yl_stem_conv(const float* x_nchw, int n, int ci, int h, int w, const void* w_packed, int ci_pad,
+                            const float* bias, const yl_tensor* y, int act, void* stream) {
+    YL_CHECK(x_nchw && w_packed && bias && y && y->data, YL_ERR_ARG, "null pointer");
+    YL_CHECK(ci >= 1 && ci <= 4, YL_ERR_UNSUPPORTED, "stem kernel takes 1..4 input channels");
+    const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+    YL_CHECK(y->dtype == YL_BF16 && y->n == n && y->h == Ho && y->w == Wo, YL_ERR_ARG, "stem output shape mismatch");
+    YL_CHECK(y->coff % 8 == 0 && y->cstride % 8 == 0, YL_ERR_ARG, "stem output needs 8-channel alignment");
+    dim3 grid((unsigned)yl::ceil_div(Wo, 32), (unsigned)yl::ceil_div(Ho, 8), (unsigned)n), block(32, 8, 1);
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
+    const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w_packed);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (y->c) {
+        case 16: yl::stem_conv_kernel<16><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
+        case 32: yl::stem_conv_kernel<32><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
+        case 48: yl::stem_conv_kernel<48><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
+        case 64: yl::stem_conv_kernel<64><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
+        case 96: yl::stem_conv_kernel<96><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
+        default:
+            yl::set_error("stem kernel is built for 16/32/48/64/96 output channels (yolo11 n/s/-/m,l/x), got %d", y->c);
+            return YL_ERR_UNSUPPORTED;
+    }
+    YL_LAUNCH_OK("stem_conv_kernel");
+    return YL_OK;
+}

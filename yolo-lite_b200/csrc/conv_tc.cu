@@ -29,16 +29,18 @@ namespace yl {
 struct ConvTcParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
-    int Ho, Wo;             // conv output dims per image (flat: 1, total pixels)
-    int tiles_w, tiles_h;   // tiles per image
-    int TW, TH;             // TW * TH == 128
+    int Ho, Wo, Nimg;            // conv output dims per image, images (flat mode: 1, total pixels, 1)
+    int tiles_w, tiles_h, tiles_n;
+    int TW, TH, TN;              // A-tile box: TW*TH*TN <= 128 rows (pixels), may span images
+    int m_tiles, n_tiles, total_tiles;
     int ksize, stride, pad;
-    int ci_pad;             // K elements per tap in the packed weights
-    int kblk, cin_blocks;   // channels per k-iteration, iterations per tap
-    int co_tile;            // UMMA N
-    int stages;
+    int ci_pad;                  // K elements per tap in the packed weights
+    int kblk, cin_blocks;        // channels per k-iteration, iterations per tap
+    int co_tile;                 // UMMA N
+    int stages, acc_stages;
     uint32_t tmem_cols;
-    uint32_t a_bytes, b_bytes;  // per-stage bytes (b rounded up to 1024)
+    uint32_t a_bytes, b_bytes;   // per-stage smem footprint (1024-aligned)
+    uint32_t tx_bytes;           // bytes one stage's two TMA boxes deliver
     // epilogue
     void* y;
     long long y_cstride;
@@ -53,19 +55,13 @@ struct ConvTcParams {
 
 constexpr int kConvTcThreads = 192;
 
+// Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
+// tile boundaries (the smem ring never drains), and with two TMEM accumulator stages the epilogue of tile i
+// overlaps the loads and MMAs of tile i+1.
 __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // ---- tile coordinates
-    int t = blockIdx.x;
-    const int tw_i = t % p.tiles_w;
-    t /= p.tiles_w;
-    const int th_i = t % p.tiles_h;
-    const int n = t / p.tiles_h;
-    const int w0 = tw_i * p.TW, h0 = th_i * p.TH;
-    const int n0 = blockIdx.y * p.co_tile;
 
     // ---- shared memory carve-up (1024-B aligned: required by the 128-B swizzle atom)
     const uint32_t raw = smem_u32(smem_raw);
@@ -74,15 +70,19 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
     uint8_t* sB = base + (size_t)p.stages * p.a_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* tmem_full_bar = empty_bar + p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tfull_bar = empty_bar + p.stages;   // [acc_stages] accumulator ready for the epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;         // [acc_stages] accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -104,27 +104,35 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)(128 * p.kblk * 2 + p.co_tile * p.kblk * 2);
             int it = 0;
-            for (int tap = 0; tap < taps; ++tap) {
-                const int r = tap / p.ksize, s = tap % p.ksize;
-                const int offh = r - p.pad, offw = s - p.pad;
-                int map = 0, dh = offh, dw = offw;
-                if (p.stride == 2) {
-                    const int ph = offh & 1, pw = offw & 1;
-                    map = ph * 2 + pw;
-                    dh = (offh - ph) >> 1;
-                    dw = (offw - pw) >> 1;
-                }
-                for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
-                    const int st = it % p.stages;
-                    const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
-                    mbar_wait(&empty_bar[st], ph_bit ^ 1u);
-                    mbar_expect_tx(&full_bar[st], tx);
-                    tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[map], &full_bar[st], cb * p.kblk, w0 + dw,
-                                h0 + dh, n);
-                    tma_load_2d(sB + (size_t)st * p.b_bytes, &p.tmB, &full_bar[st], tap * p.ci_pad + cb * p.kblk,
-                                n0);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                int mt = tile / p.n_tiles;
+                const int w0 = (mt % p.tiles_w) * p.TW;
+                mt /= p.tiles_w;
+                const int h0 = (mt % p.tiles_h) * p.TH;
+                const int i0 = (mt / p.tiles_h) * p.TN;
+                const int n0 = nt * p.co_tile;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int r = tap / p.ksize, s = tap - r * p.ksize;
+                    const int offh = r - p.pad, offw = s - p.pad;
+                    int map = 0, dh = offh, dw = offw;
+                    if (p.stride == 2) {
+                        const int ph = offh & 1, pw = offw & 1;
+                        map = ph * 2 + pw;
+                        dh = (offh - ph) >> 1;
+                        dw = (offw - pw) >> 1;
+                    }
+                    for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
+                        const int st = it % p.stages;
+                        const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
+                        mbar_wait(&empty_bar[st], ph_bit ^ 1u);
+                        mbar_expect_tx(&full_bar[st], p.tx_bytes);
+                        tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[map], &full_bar[st], cb * p.kblk, w0 + dw,
+                                    h0 + dh, i0);
+                        tma_load_2d(sB + (size_t)st * p.b_bytes, &p.tmB, &full_bar[st],
+                                    tap * p.ci_pad + cb * p.kblk, n0);
+                    }
                 }
             }
         }
@@ -134,82 +142,109 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
             const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.co_tile);
             const uint32_t row_bytes = (uint32_t)p.kblk * 2u;
             const int ksteps = p.kblk / 16;
-            for (int it = 0; it < kiters; ++it) {
-                const int st = it % p.stages;
-                const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(&full_bar[st], ph_bit);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+                const int acc = lt % p.acc_stages;
+                const uint32_t acc_ph = (uint32_t)(lt / p.acc_stages) & 1u;
+                mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t da = umma_desc_kmajor(smem_u32(sA + (size_t)st * p.a_bytes), row_bytes);
-                const uint64_t db = umma_desc_kmajor(smem_u32(sB + (size_t)st * p.b_bytes), row_bytes);
-                for (int k = 0; k < ksteps; ++k) {
-                    // advance 16 bf16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                              (it > 0 || k > 0) ? 1u : 0u);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.co_tile);
+                for (int ki = 0; ki < kiters; ++ki, ++it) {
+                    const int st = it % p.stages;
+                    const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(&full_bar[st], ph_bit);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_kmajor(smem_u32(sA + (size_t)st * p.a_bytes), row_bytes);
+                    const uint64_t db = umma_desc_kmajor(smem_u32(sB + (size_t)st * p.b_bytes), row_bytes);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // advance 16 bf16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (ki > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[st]);
                 }
-                umma_commit(&empty_bar[st]);
+                umma_commit(&tfull_bar[acc]);
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
         // ================= epilogue =================
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         const int row = q * 32 + lane;
-        const int th = row / p.TW, tw = row - th * p.TW;
-        const int h = h0 + th, w = w0 + tw;
-        const bool pvalid = (h < p.Ho) && (w < p.Wo);
-        const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
+        const int tw = row % p.TW;
+        const int th = (row / p.TW) % p.TH;
+        const int tn = row / (p.TW * p.TH);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+            const int nt = tile % p.n_tiles;
+            int mt = tile / p.n_tiles;
+            const int w = (mt % p.tiles_w) * p.TW + tw;
+            mt /= p.tiles_w;
+            const int h = (mt % p.tiles_h) * p.TH + th;
+            const int n = (mt / p.tiles_h) * p.TN + tn;
+            const int n0 = nt * p.co_tile;
+            const bool pvalid = (tn < p.TN) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
+            const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
 
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int acc = lt % p.acc_stages;
+            const uint32_t acc_ph = (uint32_t)(lt / p.acc_stages) & 1u;
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.co_tile);
 
-        for (int c0 = 0; c0 < p.co_tile; c0 += 16) {
-            uint32_t acc[16];
-            __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
-            tmem_ld16(taddr + (uint32_t)c0, acc);
-            tmem_ld_wait();
+            for (int c0 = 0; c0 < p.co_tile; c0 += 16) {
+                uint32_t accv[16];
+                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
+                tmem_ld16(taddr + (uint32_t)c0, accv);
+                tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int cb = n0 + c0 + half * 8;
-                if (!pvalid || cb >= p.y_c) continue;
-                float v[8];
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                for (int half = 0; half < 2; ++half) {
+                    const int cb = n0 + c0 + half * 8;
+                    if (!pvalid || cb >= p.y_c) continue;
+                    float v[8];
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float x = __uint_as_float(acc[half * 8 + i]) + bb[i];
-                    v[i] = p.act ? silu_f(x) : x;
-                }
-                if (p.res) {
-                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + cb));
-                    v[0] += bf16lo_f(rv.x); v[1] += bf16hi_f(rv.x);
-                    v[2] += bf16lo_f(rv.y); v[3] += bf16hi_f(rv.y);
-                    v[4] += bf16lo_f(rv.z); v[5] += bf16hi_f(rv.z);
-                    v[6] += bf16lo_f(rv.w); v[7] += bf16hi_f(rv.w);
-                }
-                const int reps = p.upsample ? 4 : 1;
-                for (int rep = 0; rep < reps; ++rep) {
-                    long long opix = pix;
-                    if (p.upsample) {
-                        const int dy = rep >> 1, dx = rep & 1;
-                        opix = ((long long)n * (2 * p.Ho) + (2 * h + dy)) * (2 * p.Wo) + (2 * w + dx);
+                    for (int i = 0; i < 8; ++i) {
+                        float x = __uint_as_float(accv[half * 8 + i]) + bb[i];
+                        v[i] = p.act ? silu_f(x) : x;
                     }
-                    if (p.y_f32) {
-                        float* dst = reinterpret_cast<float*>(p.y) + opix * p.y_cstride + p.y_coff + cb;
-                        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
-                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.y_cstride + p.y_coff + cb;
-                        uint4 o;
-                        o.x = pack_bf16x2(v[0], v[1]);
-                        o.y = pack_bf16x2(v[2], v[3]);
-                        o.z = pack_bf16x2(v[4], v[5]);
-                        o.w = pack_bf16x2(v[6], v[7]);
-                        *reinterpret_cast<uint4*>(dst) = o;
+                    if (p.res) {
+                        const uint4 rv =
+                            __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + cb));
+                        v[0] += bf16lo_f(rv.x); v[1] += bf16hi_f(rv.x);
+                        v[2] += bf16lo_f(rv.y); v[3] += bf16hi_f(rv.y);
+                        v[4] += bf16lo_f(rv.z); v[5] += bf16hi_f(rv.z);
+                        v[6] += bf16lo_f(rv.w); v[7] += bf16hi_f(rv.w);
+                    }
+                    const int reps = p.upsample ? 4 : 1;
+                    for (int rep = 0; rep < reps; ++rep) {
+                        long long opix = pix;
+                        if (p.upsample) {
+                            const int dy = rep >> 1, dx = rep & 1;
+                            opix = ((long long)n * (2 * p.Ho) + (2 * h + dy)) * (2 * p.Wo) + (2 * w + dx);
+                        }
+                        if (p.y_f32) {
+                            float* dst = reinterpret_cast<float*>(p.y) + opix * p.y_cstride + p.y_coff + cb;
+                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            __nv_bfloat16* dst =
+                                reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.y_cstride + p.y_coff + cb;
+                            uint4 o;
+                            o.x = pack_bf16x2(v[0], v[1]);
+                            o.y = pack_bf16x2(v[2], v[3]);
+                            o.z = pack_bf16x2(v[4], v[5]);
+                            o.w = pack_bf16x2(v[6], v[7]);
+                            *reinterpret_cast<uint4*>(dst) = o;
+                        }
                     }
                 }
             }
+            // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
     }
 
@@ -220,6 +255,7 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
 
 // ------------------------------------------------------------------------------------------------ host side
 static int g_max_dyn_smem = 0;
+static int g_num_sms = 148;
 
 int init_conv_tc() {
     int dev = 0;
@@ -227,6 +263,7 @@ int init_conv_tc() {
     int max_optin = 0;
     YL_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     g_max_dyn_smem = max_optin;
+    YL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     YL_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return YL_OK;
 }
@@ -252,18 +289,29 @@ static bool encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dim
     return true;
 }
 
-static void choose_patch(int Ho, int Wo, int* TH, int* TW) {
-    // TH*TW = 128, both powers of two; minimise padded area, prefer wide tiles (longer contiguous rows).
+// A-tile box (TW, TH, TN) with TW*TH*TN <= 128 output pixels, possibly spanning images: minimise the number
+// of 128-row MMA tiles needed to cover (Wo, Ho, N); ties prefer wide boxes (longer contiguous runs).
+static void choose_patch(int Ho, int Wo, int N, int* TH, int* TW, int* TN) {
     long long best = -1;
-    for (int tw = 128; tw >= 4; tw >>= 1) {
-        int th = 128 / tw;
-        long long area = (long long)ceil_div(Ho, th) * th * (long long)ceil_div(Wo, tw) * tw;
-        if (best < 0 || area < best) {
-            best = area;
-            *TH = th;
-            *TW = tw;
+    int bw = 1, bh = 1, bn = 1;
+    for (int tw = Wo < 128 ? Wo : 128; tw >= 1; --tw) {
+        if (tw != Wo && (tw & (tw - 1))) continue;  // full width or a power of two
+        for (int th = 1; th * tw <= 128 && th <= Ho; ++th) {
+            int tn = 128 / (tw * th);
+            if (tn > N) tn = N;
+            // TN > 1 stacks the same (tw, th) window of consecutive images: the box is a 4-D hyper-rectangle
+            const long long tiles = (long long)ceil_div(Wo, tw) * ceil_div(Ho, th) * ceil_div(N, tn);
+            if (best < 0 || tiles < best) {
+                best = tiles;
+                bw = tw;
+                bh = th;
+                bn = tn;
+            }
         }
     }
+    *TW = bw;
+    *TH = bh;
+    *TN = bn;
 }
 
 bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
@@ -317,25 +365,23 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     const int co16 = ceil_div(y.c, 16) * 16;
     const int n_tiles = ceil_div(co16, 256);
     p.co_tile = ceil_div(ceil_div(co16, n_tiles), 16) * 16;
-    uint32_t cols = 32;
-    while ((int)cols < p.co_tile) cols <<= 1;
-    p.tmem_cols = cols;
 
     // M tiling + activation tensor maps
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(x.data) + x.coff;
     const uint64_t es = 2;
     const bool flat = (a->k == 1 && a->stride == 1 && !a->upsample2x);
-    int n_img;
     if (flat) {
         const uint64_t M = (uint64_t)x.n * x.h * x.w;
         YL_CHECK(M < (1ull << 31), YL_ERR_ARG, "too many pixels");
         p.Ho = 1;
         p.Wo = (int)M;
+        p.Nimg = 1;
         p.TH = 1;
         p.TW = 128;
+        p.TN = 1;
         p.tiles_h = 1;
+        p.tiles_n = 1;
         p.tiles_w = ceil_div((int)M, 128);
-        n_img = 1;
         uint64_t dims[4] = {(uint64_t)x.c, M, 1, 1};
         uint64_t str[3] = {(uint64_t)x.cstride * es, (uint64_t)x.cstride * es * M, (uint64_t)x.cstride * es * M};
         uint32_t box[4] = {(uint32_t)p.kblk, 128, 1, 1};
@@ -343,11 +389,12 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     } else {
         p.Ho = Ho;
         p.Wo = Wo;
-        choose_patch(Ho, Wo, &p.TH, &p.TW);
+        p.Nimg = x.n;
+        choose_patch(Ho, Wo, x.n, &p.TH, &p.TW, &p.TN);
         p.tiles_h = ceil_div(Ho, p.TH);
         p.tiles_w = ceil_div(Wo, p.TW);
-        n_img = x.n;
-        uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        p.tiles_n = ceil_div(x.n, p.TN);
+        uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
         if (a->stride == 1) {
             uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
             uint64_t str[3] = {(uint64_t)x.cstride * es, (uint64_t)x.cstride * es * x.w,
@@ -375,14 +422,23 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
 
     p.a_bytes = 128u * p.kblk * 2u;
     p.b_bytes = ((uint32_t)p.co_tile * p.kblk * 2u + 1023u) & ~1023u;
-    const int kiters = a->k * a->k * p.cin_blocks;
+    p.tx_bytes = (uint32_t)(p.TW * p.TH * p.TN) * p.kblk * 2u + (uint32_t)p.co_tile * p.kblk * 2u;
+    p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.n_tiles = n_tiles;
+    p.total_tiles = p.m_tiles * n_tiles;
+    // two accumulator stages whenever they fit the 512 TMEM columns; two CTAs per SM when TMEM and smem allow
+    p.acc_stages = (2 * p.co_tile <= 512) ? 2 : 1;
+    uint32_t cols = 32;
+    while ((int)cols < p.acc_stages * p.co_tile) cols <<= 1;
+    p.tmem_cols = cols;
+    const int ctas_per_sm = (cols <= 256) ? 2 : 1;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    int stages = (int)(98304u / stage_bytes);
-    if (stages > 4) stages = 4;
+    const uint32_t budget = (uint32_t)(ctas_per_sm == 2 ? 108 * 1024 : 200 * 1024);
+    int stages = (int)(budget / stage_bytes);
+    if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
-    if (stages > kiters) stages = kiters;
     p.stages = stages;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16;
     YL_CHECK((int)smem <= g_max_dyn_smem, YL_ERR_UNSUPPORTED, "conv tile needs %zu B smem (max %d)", smem,
              g_max_dyn_smem);
 
@@ -398,7 +454,8 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     p.res_coff = a->res.coff;
     p.upsample = a->upsample2x ? 1 : 0;
 
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * n_img), (unsigned)n_tiles, 1);
+    int grid = g_num_sms * ctas_per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
     conv_tc_kernel<<<grid, kConvTcThreads, smem, stream>>>(p);
     YL_LAUNCH_OK("conv_tc_kernel");
     return YL_OK;

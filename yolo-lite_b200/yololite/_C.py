@@ -69,6 +69,8 @@ _PROTOTYPES = {
     "yl_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "yl_conv_bn_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "yl_conv_tc_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "yl_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                               C.POINTER(Tensor), C.c_int, C.c_void_p]),
     "yl_dwconv3x3": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_int,
                                C.POINTER(Tensor), C.c_void_p]),
     "yl_sppf_pool": (C.c_int, [C.POINTER(Tensor)] * 4 + [C.c_int, C.c_void_p]),

@@ -27,6 +27,8 @@ def run_standalone(module, x):
             g = _plan.Builder(dev)
             statics = [torch.empty(tuple(t.shape), dtype=torch.float32, device=dev) for t in xs]
             views = [g.input_nchw(s) for s in statics]
+            if not getattr(module, "_takes_nchw", False):
+                views = g.mat(views)
             res = module._emit(g, views if multi else views[0])
             post = getattr(module, "_yl_export", None)
             outs = post(g, res) if post is not None else g.to_nchw(res)

@@ -29,6 +29,16 @@ class Dest:
         return v
 
 
+class NchwInput:
+    """The caller's NCHW fp32 batch, not yet converted.  A stem conv consumes it directly (fused ingest);
+    anything else forces the NHWC bf16 materialisation."""
+
+    def __init__(self, static: torch.Tensor):
+        self.static = static
+        self.n, self.c, self.h, self.w = static.shape
+        self.view: View | None = None
+
+
 class Builder:
     def __init__(self, device: torch.device):
         self.device = device
@@ -37,6 +47,7 @@ class Builder:
         self.buffers: list[torch.Tensor] = []
         self.bytes = 0
         self.meta: list[dict] = []
+        self.ingest: NchwInput | None = None
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -53,23 +64,46 @@ class Builder:
         assert (out.n, out.h, out.w, out.c) == (n, h, w, c), ((out.n, out.h, out.w, out.c), (n, h, w, c))
         return out
 
-    def _push(self, fn, *args, keep=(), kind="", bytes_=0, flops=0):
+    def _push(self, fn, *args, keep=(), kind="", bytes_=0, flops=0, desc=""):
         self.calls.append((fn, args, keep))
         # algorithmic work of the launch (each operand touched once): the roofline numerators of DESIGN.md
-        self.meta.append({"kind": kind or fn.__name__, "bytes": int(bytes_), "flops": int(flops)})
+        self.meta.append({"kind": kind or fn.__name__, "bytes": int(bytes_), "flops": int(flops), "desc": desc})
 
     # ------------------------------------------------------------------ ops
-    def input_nchw(self, x_nchw_static: torch.Tensor) -> View:
-        n, c, h, w = x_nchw_static.shape
-        v = self.alloc(n, h, w, c)
-        t = v.ct()
-        self._push(self.lib.yl_nchw_to_nhwc, x_nchw_static.data_ptr(), C.byref(t), keep=(t, x_nchw_static),
-                   kind="ingest_nchw_to_nhwc", bytes_=n * c * h * w * (4 + 2))
-        return v
+    def input_nchw(self, x_nchw_static: torch.Tensor) -> NchwInput:
+        self.ingest = NchwInput(x_nchw_static)
+        return self.ingest
+
+    def mat(self, x):
+        """NHWC bf16 view of `x` (materialises a pending NCHW input with the layout kernel)."""
+        if isinstance(x, (list, tuple)):
+            return [self.mat(v) for v in x]
+        if not isinstance(x, NchwInput):
+            return x
+        if x.view is None:
+            v = self.alloc(x.n, x.h, x.w, x.c)
+            t = v.ct()
+            self._push(self.lib.yl_nchw_to_nhwc, x.static.data_ptr(), C.byref(t), keep=(t, x.static),
+                       kind="ingest_nchw_to_nhwc", bytes_=x.n * x.c * x.h * x.w * (4 + 2))
+            x.view = v
+        return x.view
 
     def conv(self, x: View, pc: PackedConv, stride=1, act=True, out=None, res: View | None = None,
              upsample=False, out_dtype=torch.bfloat16, impl=_C.IMPL_AUTO) -> View:
         k = pc.k
+        if isinstance(x, NchwInput):
+            if (x.view is None and not self.calls and k == 3 and stride == 2 and x.c <= 4 and not pc.depthwise
+                    and res is None and not upsample and out_dtype is torch.bfloat16
+                    and pc.co in (16, 32, 48, 64, 96)):
+                ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+                y = self._out(out, x.n, ho, wo, pc.co)
+                yt = y.ct()
+                self._push(self.lib.yl_stem_conv, x.static.data_ptr(), x.n, x.c, x.h, x.w, pc.w.data_ptr(), pc.ci_pad,
+                           pc.bias.data_ptr(), C.byref(yt), int(act), keep=(yt, pc, x.static), kind="stem_conv",
+                           bytes_=x.n * x.c * x.h * x.w * 4 + x.n * ho * wo * pc.co * 2,
+                           flops=2 * x.n * ho * wo * pc.co * x.c * 9, desc=f"{x.c}->{pc.co} k3s2 {x.h}x{x.w} nchw-f32 in")
+                return y
+            x = self.mat(x)
         ho = (x.h + 2 * (k // 2) - k) // stride + 1
         wo = (x.w + 2 * (k // 2) - k) // stride + 1
         u = 2 if upsample else 1
@@ -90,7 +124,9 @@ class Builder:
         self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc), kind="conv_tc" if tc else "conv_direct",
                    bytes_=x.n * x.h * x.w * x.c * 2 + opx * pc.co * esz * u * u + k * k * x.c * pc.co * 2
                    + (opx * pc.co * 2 if res is not None else 0),
-                   flops=2 * opx * pc.co * x.c * k * k)
+                   flops=2 * opx * pc.co * x.c * k * k,
+                   desc=f"{x.c}->{pc.co} k{k}s{stride} {x.h}x{x.w}" + (" +res" if res is not None else "")
+                   + (" up2" if upsample else "") + (" f32" if esz == 4 else ""))
         return y
 
     def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):
@@ -99,6 +135,7 @@ class Builder:
                    bytes_=x.n * x.h * x.w * x.c * 2 * 4)
 
     def upsample2x(self, x: View, out=None) -> View:
+        x = self.mat(x)
         y = self._out(out, x.n, 2 * x.h, 2 * x.w, x.c)
         xt, yt = x.ct(), y.ct()
         self._push(self.lib.yl_upsample2x, C.byref(xt), C.byref(yt), keep=(xt, yt), kind="upsample2x",
@@ -106,6 +143,7 @@ class Builder:
         return y
 
     def copy(self, x: View, out=None) -> View:
+        x = self.mat(x)
         y = self._out(out, x.n, x.h, x.w, x.c)
         xt, yt = x.ct(), y.ct()
         self._push(self.lib.yl_copy_slice, C.byref(xt), C.byref(yt), keep=(xt, yt), kind="copy_slice",
@@ -133,6 +171,7 @@ class Builder:
         return y
 
     def to_nchw(self, x: View) -> torch.Tensor:
+        x = self.mat(x)
         out = torch.empty((x.n, x.c, x.h, x.w), dtype=torch.float32, device=self.device)
         self.buffers.append(out)
         xt = x.ct()
@@ -164,7 +203,8 @@ class Plan:
         first = 0
         if self.graph is not None or ingest_ptr is not None:
             for fn, args, _ in self.calls[: self._skip if self.graph is not None else 1]:
-                a = (ingest_ptr,) + tuple(args[1:]) if (ingest_ptr is not None and fn.__name__ == "yl_nchw_to_nhwc") else args
+                a = (ingest_ptr,) + tuple(args[1:]) if (ingest_ptr is not None and
+                                                         fn.__name__ in ("yl_nchw_to_nhwc", "yl_stem_conv")) else args
                 _C.check(fn(*a, s), fn.__name__)
             first = self._skip if self.graph is not None else 1
         if self.graph is not None:

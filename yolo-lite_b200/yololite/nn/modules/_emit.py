@@ -17,6 +17,9 @@ from ... import _lazy
 class YLModule(nn.Module):
     """Base: plan-cached standalone forward + cache invalidation when parameters move or reload."""
 
+    #: True for modules whose _emit accepts the raw NCHW fp32 input (the fused stem conv)
+    _takes_nchw = False
+
     def _emit(self, g, x, out=None):  # pragma: no cover - abstract
         raise NotImplementedError
 
@@ -79,6 +82,8 @@ def act_flag(act: nn.Module) -> bool:
 
 def emit_any(g, m: nn.Module, x, out=None, out_dtype=torch.bfloat16):
     """Emit a yololite module, a plain nn.Conv2d (head.py:39,48: bias, no BN/act) or an nn.Sequential of them."""
+    if not getattr(m, "_takes_nchw", False) and not isinstance(m, nn.Sequential):
+        x = g.mat(x)
     if isinstance(m, nn.Sequential):
         mods = list(m)
         for i, sub in enumerate(mods):

@@ -32,6 +32,7 @@ class Conv(YLModule):
     """conv -> BatchNorm -> activation as ONE fused kernel. Args: (c1, c2, k, s, p, g, d, act)."""
 
     default_act = nn.SiLU()
+    _takes_nchw = True
 
     def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
         super().__init__()
