@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define YL11_VERSION 100
+#define YL11_VERSION 101
 
 typedef enum yl_status {
     YL_OK = 0,
@@ -82,11 +82,15 @@ int yl_upsample2x(const yl_tensor* x, const yl_tensor* y, void* stream);
  * (block.py:233-235, 259, 184) via the output slice.  Dense k in {1,3}, stride in {1,2}, pad = k/2.
  *   y = [res +] act(conv(x, w) + bias)
  * `y.h/y.w` are the conv output dims; with upsample2x != 0 each result pixel is replicated into the 2x2
- * block of a (n, 2h, 2w) buffer described by `y` (then y.h/y.w are the *upsampled* dims). */
+ * block of a (n, 2h, 2w) buffer described by `y` (then y.h/y.w are the *upsampled* dims).
+ * The tcgen05 path stores through TMA: out-of-range rows/channels are clipped by the tensor map. */
 typedef struct yl_conv_args {
     yl_tensor x;
     yl_tensor y;   /* bf16 or f32 */
     yl_tensor res; /* res.data == NULL: no residual; else same dims as the conv output, bf16 */
+    yl_tensor y_up; /* y_up.data == NULL: none; else a second destination (n, 2h, 2w) of y's dtype that
+                       receives the result replicated 2x2: a conv output that feeds both a Concat and an
+                       nn.Upsample -> Concat (cfg/yolo11.yaml:31-44) is stored once per consumer        */
     const void* w; /* packed by yl_fold_bn_pack                                              */
     const float* bias;
     int32_t k, stride;

@@ -52,7 +52,49 @@ CONV_CASES = [
     (128, 256, 3, 2, 1, 24, 40, True, False, False, 0, 128, False, "k3_s2_co256"),
     (256, 128, 1, 1, 1, 10, 10, True, False, True, 0, 128, False, "k1_upsample_into_concat"),
     (64, 64, 3, 1, 1, 8, 8, True, False, True, 0, 0, False, "k3_upsample"),
+    (96, 48, 1, 1, 3, 20, 20, True, False, False, 0, 16, False, "k1_co48_chunk_tail"),
+    (64, 144, 1, 1, 1, 20, 20, False, False, False, 0, 0, True, "k1_co144_f32_multichunk"),
+    (64, 64, 3, 1, 9, 20, 20, True, True, False, 0, 64, False, "k3_20x20_stacked_images_res"),
+    (32, 32, 1, 1, 5, 23, 17, True, True, False, 0, 0, False, "k1_flat_ragged_tail_res"),
+    (128, 256, 3, 1, 2, 20, 20, True, False, False, 0, 0, False, "k3_co256_long_k"),
 ]
+
+DUAL_CASES = [
+    # ci, co, k, s, n, h, w, y_pad, up_pad, tag
+    (256, 256, 1, 1, 2, 20, 20, 0, 128, "k1_dual_concat"),
+    (64, 128, 3, 2, 3, 16, 24, 128, 64, "k3s2_dual_slices"),
+    (32, 16, 3, 1, 1, 12, 12, 0, 0, "k3_dual_co16"),
+]
+
+
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[c[-1] for c in DUAL_CASES])
+@pytest.mark.parametrize("impl", ["tc", "direct"])
+def test_conv_dual_destination(ops, case, impl):
+    """y_up: the result is stored at conv resolution AND 2x2-replicated into a second buffer (Upsample fused)."""
+    from yololite import _C
+
+    ci, co, k, s, n, h, w, y_pad, up_pad, tag = case
+    g = torch.Generator().manual_seed(zlib.crc32(tag.encode()) % 2**31)
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, k, k, generator=g) * (1.5 / (ci * k * k) ** 0.5)
+    bias = torch.randn(co, generator=g) * 0.1
+    pc = ops.pack_conv(wt, bn=None, conv_bias=bias)
+    ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
+    ref = F.silu(F.conv2d(bf16r(x), bf16r(wt), bias, s, k // 2))
+    xv = ops.View(nhwc(x), 0, ci)
+    yb = torch.full((n, ho, wo, co + y_pad), -3.0, dtype=torch.bfloat16, device="cuda")
+    ub = torch.full((n, 2 * ho, 2 * wo, co + up_pad), -3.0, dtype=torch.bfloat16, device="cuda")
+    yv, uv = ops.View(yb, y_pad // 2, co), ops.View(ub, up_pad // 2, co)
+    ops.conv(xv, yv, pc, s, True, None, False, impl=_C.IMPL_TCGEN05 if impl == "tc" else _C.IMPL_DIRECT, y_up=uv)
+    torch.cuda.synchronize()
+    got = yv.torch_nhwc().float().cpu().permute(0, 3, 1, 2)
+    got_up = uv.torch_nhwc().float().cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-2, atol=2e-2)
+    np.testing.assert_array_equal(got_up.numpy(), F.interpolate(got, scale_factor=2.0, mode="nearest").numpy())
+    for buf, pad in ((yb, y_pad), (ub, up_pad)):
+        if pad:
+            rest = torch.cat([buf[..., : pad // 2], buf[..., pad // 2 + co:]], -1)
+            assert bool((rest == -3.0).all())
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[-1] for c in CONV_CASES])

@@ -24,6 +24,9 @@ struct ConvDirectParams {
     long long res_cstride;
     int res_coff;
     int N, Ho, Wo, k, stride, pad, act, upsample;
+    void* y_up;  // optional second destination (n, 2Ho, 2Wo): result replicated 2x2
+    long long yu_cstride;
+    int yu_coff;
 };
 
 __global__ void __launch_bounds__(256) conv_direct_kernel(const ConvDirectParams p) {
@@ -73,6 +76,17 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const ConvDirectParams
             else
                 reinterpret_cast<__nv_bfloat16*>(p.y)[opix * p.y_cstride + p.y_coff + c] = __float2bfloat16_rn(v);
         }
+        if (p.y_up) {
+            for (int rep = 0; rep < 4; ++rep) {
+                const long long opix =
+                    ((long long)n * (2 * p.Ho) + (2 * ho + (rep >> 1))) * (2 * p.Wo) + (2 * wo + (rep & 1));
+                if (p.y_f32)
+                    reinterpret_cast<float*>(p.y_up)[opix * p.yu_cstride + p.yu_coff + c] = v;
+                else
+                    reinterpret_cast<__nv_bfloat16*>(p.y_up)[opix * p.yu_cstride + p.yu_coff + c] =
+                        __float2bfloat16_rn(v);
+            }
+        }
     }
 }
 
@@ -120,6 +134,13 @@ int launch_conv_direct(const yl_conv_args* a, cudaStream_t stream) {
     p.pad = pad;
     p.act = a->act;
     p.upsample = a->upsample2x ? 1 : 0;
+    p.y_up = a->y_up.data;
+    p.yu_cstride = a->y_up.cstride;
+    p.yu_coff = a->y_up.coff;
+    if (a->y_up.data)
+        YL_CHECK(!a->upsample2x && a->y_up.n == x.n && a->y_up.h == 2 * Ho && a->y_up.w == 2 * Wo &&
+                     a->y_up.c == y.c && a->y_up.dtype == y.dtype,
+                 YL_ERR_ARG, "y_up must be the (n, 2h, 2w, c) twin of y");
     const long long total = (long long)x.n * Ho * Wo;
     dim3 grid((unsigned)ceil_div64(total, 256), (unsigned)ceil_div(y.c, 8), 1);
     conv_direct_kernel<<<grid, 256, 0, stream>>>(p);

@@ -1,10 +1,11 @@
-// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands fed by TMA.
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands fed AND results drained by
+// TMA.
 //
 //   D[M = 128 output pixels, N = co_tile] = sum over taps (r,s) and channel blocks of
 //       A[pixels shifted by the tap, kblk channels]  x  W[co_tile, kblk]
 //
-// * activations are NHWC bf16; the A tile of one tap is a TH x TW spatial patch of one image fetched by a
-//   single 4-D TMA box {kblk, TW, TH, 1}; the conv halo and ragged image edges are TMA out-of-bounds
+// * activations are NHWC bf16; the A tile of one tap is a TH x TW spatial patch of TN images fetched by a
+//   single 4-D TMA box {kblk, TW, TH, TN}; the conv halo and ragged image edges are TMA out-of-bounds
 //   zero fill (signed coordinates), so there is no im2col buffer and no padding pass;
 // * stride-2 convs read one of four "parity planes" (h%2, w%2) of the input, each its own 4-D tensor map,
 //   so a tap is again a dense box;
@@ -12,14 +13,18 @@
 // * weights are packed [co][tap][ci] bf16 (K-major), fetched by a 2-D TMA box {kblk, co_tile};
 // * both tiles land in the canonical K-major swizzled layout (SW128/64/32 for kblk 64/32/16) that
 //   tcgen05.mma reads through shared-memory descriptors; accumulation is fp32 in TMEM;
-// * epilogue (4 warps, one TMEM lane quadrant each): tcgen05.ld -> +bias -> SiLU -> +residual -> bf16/f32
-//   store into a channel slice of the destination (concat = aliasing), optionally replicated 2x2
-//   (nearest upsample fused into the producer).
+// * epilogue: two groups of 4 warps, group g owns TMEM accumulator stage g (tiles alternate between the
+//   groups).  Per 32-column chunk: tcgen05.ld -> +bias (smem) -> SiLU (1 MUFU) -> +residual -> bf16/f32 ->
+//   swizzled staging tile in smem -> ONE TMA store of the {chunk, TW, TH, TN} box into the channel slice of
+//   the destination (concat = aliasing; ragged rows / channel tails are clipped by the tensor map).  The
+//   nearest-2x upsample is four more TMA stores of the same staging tile into the parity planes of the
+//   upsampled destination, so a result that feeds both a Concat and an Upsample->Concat is computed once.
 //
 // Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
-// warps 2..5 = epilogue.  Pipeline: `stages`-deep smem ring with full/empty mbarriers; tcgen05.commit
-// releases a stage back to the producer and finally signals the epilogue.
+// warps 2..9 = epilogue.  Pipeline: `stages`-deep smem ring with full/empty mbarriers; tcgen05.commit
+// releases a stage back to the producer and finally signals the epilogue group of that accumulator.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -29,6 +34,8 @@ namespace yl {
 struct ConvTcParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
+    CUtensorMap tmY[5];          // [0] plain destination, [1..4] parity planes of the 2x-upsampled destination
+    int y_map_first, y_map_last; // stores go to tmY[first..last)
     int Ho, Wo, Nimg;            // conv output dims per image, images (flat mode: 1, total pixels, 1)
     int tiles_w, tiles_h, tiles_n;
     int TW, TH, TN;              // A-tile box: TW*TH*TN <= 128 rows (pixels), may span images
@@ -37,28 +44,157 @@ struct ConvTcParams {
     int ci_pad;                  // K elements per tap in the packed weights
     int kblk, cin_blocks;        // channels per k-iteration, iterations per tap
     int co_tile;                 // UMMA N
-    int stages, acc_stages;
+    int acc_stride;              // TMEM columns per accumulator stage (co_tile rounded up to the chunk width)
+    int stages;
+    // halo-patch mode (3x3 stride 1, thin channels): ONE TMA box {kblk, patch_pw, TH+2} per tile holds every
+    // tap's A operand (taps are shifted windows of it); the 9-tap weights stay resident in smem
+    int patch, patch_pw, patch_bo;
+    CUtensorMap tmW3;            // weights as {ci, co, tap}: box {kblk, co_tile, 9} -> smem [tap][co_tile][kblk]
+    uint32_t w_bytes;
     uint32_t tmem_cols;
     uint32_t a_bytes, b_bytes;   // per-stage smem footprint (1024-aligned)
     uint32_t tx_bytes;           // bytes one stage's two TMA boxes deliver
     // epilogue
-    void* y;
-    long long y_cstride;
-    int y_coff, y_c, y_f32;
+    int cw;                      // columns per chunk (16 or 32)
+    int nchunks;
+    int stg_row_bytes;           // cw * element size: 32, 64 or 128 (= the staging swizzle span)
+    uint32_t stg_bytes;          // per epilogue group
+    int y_f32;
     const float* bias;
+    int n_bias;                  // valid bias entries (co_pad)
     int act;
     const __nv_bfloat16* res;
     long long res_cstride;
-    int res_coff;
-    int upsample;
+    int res_coff, res_c;
 };
 
-constexpr int kConvTcThreads = 192;
+constexpr int kConvTcThreads = 320;
+constexpr int kEpiGroupThreads = 128;
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[CW]);
+template <>
+__device__ __forceinline__ void tmem_ld_cw<16>(uint32_t taddr, uint32_t (&r)[16]) {
+    tmem_ld16(taddr, r);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cw<32>(uint32_t taddr, uint32_t (&r)[32]) {
+    tmem_ld32(taddr, r);
+}
+
+// One epilogue group (4 warps, thread = accumulator row) draining the tiles of its accumulator stage.
+template <int CW>
+__device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, int q, int lane, int gtid,
+                                                 uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                 uint8_t* stg, const float* sbias) {
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const uint32_t swz_mask = (uint32_t)(p.stg_row_bytes / 16 - 1);  // 1, 3 or 7 sixteen-byte chunks
+    const uint32_t row_off = (uint32_t)row * (uint32_t)p.stg_row_bytes;
+    const uint32_t stg_base = smem_u32(stg);
+
+    int lt = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, lt += 2) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.TW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.TH;
+        const int i0 = (mt / p.tiles_h) * p.TN;
+        const int n0 = nt * p.co_tile;
+
+        const __nv_bfloat16* resrow = nullptr;
+        if (p.res) {
+            const int w = w0 + tw, h = h0 + th, n = i0 + tn;
+            if ((tn < p.TN) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo))
+                resrow = p.res + (((long long)n * p.Ho + h) * p.Wo + w) * p.res_cstride + p.res_coff;
+        }
+
+        const uint32_t ph = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(&tfull_bar[g], ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.acc_stride);
+
+        for (int c = 0; c < p.nchunks; ++c) {
+            const int col0 = n0 + c * CW;  // first output channel of this chunk
+            uint32_t acc[CW];
+            tmem_ld_cw<CW>(taddr + (uint32_t)(c * CW), acc);
+            // residual rows are independent of the accumulator: issue the loads under the TMEM latency
+            uint4 rv[CW / 8];
+#pragma unroll
+            for (int i = 0; i < CW / 8; ++i) {
+                rv[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (resrow && col0 + i * 8 < p.res_c) rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
+            }
+            tmem_ld_wait();
+            if (c == p.nchunks - 1) {
+                // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[g]);
+            }
+            float v[CW];
+#pragma unroll
+            for (int i = 0; i < CW; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + i);
+                v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
+                v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+                v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
+                v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+            }
+            if (p.act) {
+#pragma unroll
+                for (int i = 0; i < CW; ++i) v[i] = silu_fast(v[i]);
+            }
+            if (p.res) {
+#pragma unroll
+                for (int i = 0; i < CW / 8; ++i) {
+                    v[i * 8 + 0] += bf16lo_f(rv[i].x); v[i * 8 + 1] += bf16hi_f(rv[i].x);
+                    v[i * 8 + 2] += bf16lo_f(rv[i].y); v[i * 8 + 3] += bf16hi_f(rv[i].y);
+                    v[i * 8 + 4] += bf16lo_f(rv[i].z); v[i * 8 + 5] += bf16hi_f(rv[i].z);
+                    v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
+                }
+            }
+            // the previous TMA store of this group must have finished reading the staging tile
+            if (gtid == 0) bulk_wait_read<0>();
+            named_bar_sync(1 + g, kEpiGroupThreads);
+            if (p.y_f32) {
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                    uint32_t off = row_off + (uint32_t)j * 16u;
+                    off ^= ((off >> 7) & swz_mask) << 4;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + off), "f"(v[4 * j]),
+                                 "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                 : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) {
+                    uint32_t off = row_off + (uint32_t)j * 16u;
+                    off ^= ((off >> 7) & swz_mask) << 4;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + off),
+                                 "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                                 "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                                 : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + g, kEpiGroupThreads);
+            if (gtid == 0) {
+                for (int m = p.y_map_first; m < p.y_map_last; ++m) tma_store_4d(&p.tmY[m], stg, col0, w0, h0, i0);
+                bulk_commit();
+            }
+        }
+    }
+    if (gtid == 0) bulk_wait<0>();
+}
 
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
 // tile boundaries (the smem ring never drains), and with two TMEM accumulator stages the epilogue of tile i
-// overlaps the loads and MMAs of tile i+1.
-__global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+// overlaps the loads and MMAs of tiles i+1, i+2.
+__global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -67,12 +203,16 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* sA = base;
-    uint8_t* sB = base + (size_t)p.stages * p.a_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_bytes);
+    uint8_t* sB = sA + (size_t)p.stages * p.a_bytes;
+    uint8_t* sStg = sB + (p.patch ? (size_t)p.b_bytes : (size_t)p.stages * p.b_bytes);  // [2 groups][stg_bytes]
+    float* sbias = reinterpret_cast<float*>(sStg + 2 * (size_t)p.stg_bytes);
+    const int nbias = p.n_tiles * p.co_tile + 32;                          // chunk tails read past co_tile
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + ((nbias + 3) & ~3));
     uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* tfull_bar = empty_bar + p.stages;   // [acc_stages] accumulator ready for the epilogue
-    uint64_t* tempty_bar = tfull_bar + 2;         // [acc_stages] accumulator drained by the epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* tfull_bar = empty_bar + p.stages;   // [2] accumulator ready for its epilogue group
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+    uint64_t* w_bar = tempty_bar + 2;             // patch mode: resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -81,8 +221,9 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp of the group
         }
+        mbar_init(w_bar, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -92,7 +233,9 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA[0]);
         tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmY[p.y_map_first]);
     }
+    for (int i = threadIdx.x; i < nbias; i += blockDim.x) sbias[i] = i < p.n_bias ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -103,7 +246,23 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (lane == 0 && p.patch) {
+            mbar_expect_tx(w_bar, p.w_bytes);
+            tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                int mt = tile;
+                const int w0 = (mt % p.tiles_w) * p.TW;
+                mt /= p.tiles_w;
+                const int h0 = (mt % p.tiles_h) * p.TH;
+                const int i0 = mt / p.tiles_h;
+                const int st = it % p.stages;
+                const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(&empty_bar[st], ph_bit ^ 1u);
+                mbar_expect_tx(&full_bar[st], p.tx_bytes);
+                tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[0], &full_bar[st], 0, w0 - 1, h0 - 1, i0);
+            }
+        } else if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
@@ -138,17 +297,50 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && p.patch) {
+            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.co_tile);
+            const uint32_t rb = (uint32_t)p.kblk * 2u;
+            const int ksteps = p.kblk / 16;
+            const uint32_t sbo = (uint32_t)p.patch_pw * rb;       // next 8-row group = next patch row (TW == 8)
+            const uint32_t wtap = (uint32_t)p.co_tile * rb;       // bytes of one tap's weight tile
+            mbar_wait(w_bar, 0);
+            tc_fence_after();
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+                mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+                const int st = lt % p.stages;
+                mbar_wait(&full_bar[st], (uint32_t)(lt / p.stages) & 1u);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA + (size_t)st * p.a_bytes);
+                const uint32_t b0 = smem_u32(sB);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int r = tap / 3, s = tap - 3 * r;
+                    const uint32_t astart = a0 + (uint32_t)(r * p.patch_pw + s) * rb;
+                    const uint32_t bo = p.patch_bo ? ((astart >> 7) & 7u) : 0u;
+                    const uint64_t da = umma_desc_kmajor_ex(astart, rb, sbo, bo);
+                    const uint64_t db = umma_desc_kmajor(b0 + (uint32_t)tap * wtap, rb);
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (tap > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[st]);
+                umma_commit(&tfull_bar[acc]);
+            }
+        } else if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.co_tile);
             const uint32_t row_bytes = (uint32_t)p.kblk * 2u;
             const int ksteps = p.kblk / 16;
             int it = 0, lt = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-                const int acc = lt % p.acc_stages;
-                const uint32_t acc_ph = (uint32_t)(lt / p.acc_stages) & 1u;
+                const int acc = lt & 1;
+                const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.co_tile);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
                     const int st = it % p.stages;
                     const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
@@ -168,84 +360,15 @@ __global__ void __launch_bounds__(kConvTcThreads) conv_tc_kernel(const __grid_co
         }
     } else {
         // ================= epilogue =================
+        const int e = warp - 2;
+        const int g = e >> 2;    // epilogue group = accumulator stage
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
-        const int row = q * 32 + lane;
-        const int tw = row % p.TW;
-        const int th = (row / p.TW) % p.TH;
-        const int tn = row / (p.TW * p.TH);
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-            const int nt = tile % p.n_tiles;
-            int mt = tile / p.n_tiles;
-            const int w = (mt % p.tiles_w) * p.TW + tw;
-            mt /= p.tiles_w;
-            const int h = (mt % p.tiles_h) * p.TH + th;
-            const int n = (mt / p.tiles_h) * p.TN + tn;
-            const int n0 = nt * p.co_tile;
-            const bool pvalid = (tn < p.TN) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
-            const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
-
-            const int acc = lt % p.acc_stages;
-            const uint32_t acc_ph = (uint32_t)(lt / p.acc_stages) & 1u;
-            mbar_wait(&tfull_bar[acc], acc_ph);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.co_tile);
-
-            for (int c0 = 0; c0 < p.co_tile; c0 += 16) {
-                uint32_t accv[16];
-                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
-                tmem_ld16(taddr + (uint32_t)c0, accv);
-                tmem_ld_wait();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int cb = n0 + c0 + half * 8;
-                    if (!pvalid || cb >= p.y_c) continue;
-                    float v[8];
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float x = __uint_as_float(accv[half * 8 + i]) + bb[i];
-                        v[i] = p.act ? silu_f(x) : x;
-                    }
-                    if (p.res) {
-                        const uint4 rv =
-                            __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + cb));
-                        v[0] += bf16lo_f(rv.x); v[1] += bf16hi_f(rv.x);
-                        v[2] += bf16lo_f(rv.y); v[3] += bf16hi_f(rv.y);
-                        v[4] += bf16lo_f(rv.z); v[5] += bf16hi_f(rv.z);
-                        v[6] += bf16lo_f(rv.w); v[7] += bf16hi_f(rv.w);
-                    }
-                    const int reps = p.upsample ? 4 : 1;
-                    for (int rep = 0; rep < reps; ++rep) {
-                        long long opix = pix;
-                        if (p.upsample) {
-                            const int dy = rep >> 1, dx = rep & 1;
-                            opix = ((long long)n * (2 * p.Ho) + (2 * h + dy)) * (2 * p.Wo) + (2 * w + dx);
-                        }
-                        if (p.y_f32) {
-                            float* dst = reinterpret_cast<float*>(p.y) + opix * p.y_cstride + p.y_coff + cb;
-                            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
-                            __nv_bfloat16* dst =
-                                reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.y_cstride + p.y_coff + cb;
-                            uint4 o;
-                            o.x = pack_bf16x2(v[0], v[1]);
-                            o.y = pack_bf16x2(v[2], v[3]);
-                            o.z = pack_bf16x2(v[4], v[5]);
-                            o.w = pack_bf16x2(v[6], v[7]);
-                            *reinterpret_cast<uint4*>(dst) = o;
-                        }
-                    }
-                }
-            }
-            // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
+        const int gtid = (e & 3) * 32 + lane;
+        uint8_t* stg = sStg + (size_t)g * p.stg_bytes;
+        if (p.cw == 32)
+            conv_tc_epilogue<32>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
+        else
+            conv_tc_epilogue<16>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
     }
 
     tc_fence_before();
@@ -268,17 +391,16 @@ int init_conv_tc() {
     return YL_OK;
 }
 
-static bool encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, CUtensorMapSwizzle sw) {
+static bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) {
         set_error("yl_init() was not called (TMA encoder unresolved)");
         return false;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r,
                   rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
@@ -287,6 +409,11 @@ static bool encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dim
         return false;
     }
     return true;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 // A-tile box (TW, TH, TN) with TW*TH*TN <= 128 output pixels, possibly spanning images: minimise the number
@@ -332,10 +459,48 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
     if (a->stride == 2 && ((x.h | x.w) & 1)) NOPE("stride 2 needs even input dims");
     if (a->res.data && (a->res.c % 8 || a->res.coff % 8 || a->res.cstride % 8 || a->res.dtype != YL_BF16))
         NOPE("residual must be bf16 with 8-channel alignment");
-    if (((uintptr_t)x.data | (uintptr_t)y.data | (uintptr_t)a->w | (uintptr_t)a->bias | (uintptr_t)a->res.data) & 15)
+    if (a->y_up.data && (a->y_up.c != y.c || a->y_up.coff % 8 || a->y_up.cstride % 8 || a->y_up.dtype != y.dtype))
+        NOPE("y_up must match y's channels and dtype with 8-channel alignment");
+    if (a->y_up.data && a->upsample2x) NOPE("y_up and upsample2x are mutually exclusive");
+    if (((uintptr_t)x.data | (uintptr_t)y.data | (uintptr_t)a->w | (uintptr_t)a->bias | (uintptr_t)a->res.data |
+         (uintptr_t)a->y_up.data) & 15)
         NOPE("pointers must be 16-byte aligned");
     return true;
 #undef NOPE
+}
+
+// Tensor maps of a destination of conv-output resolution (Ho, Wo) [up == 0, one map] or of the 2x-upsampled
+// resolution [up == 1, four parity-plane maps]; flat mode describes the pixel axis as one dimension.
+static bool encode_out_maps(CUtensorMap* maps, const yl_tensor& y, int Ho, int Wo, int N, bool flat, bool up,
+                            const uint32_t* box, CUtensorMapSwizzle sw) {
+    const uint64_t es = (y.dtype == YL_F32) ? 4 : 2;
+    const CUtensorMapDataType dt = (y.dtype == YL_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    uint8_t* yb = reinterpret_cast<uint8_t*>(y.data) + (size_t)y.coff * es;
+    const uint64_t cs = (uint64_t)y.cstride * es;
+    if (!up) {
+        if (flat) {
+            const uint64_t M = (uint64_t)N * Ho * Wo;
+            uint64_t dims[4] = {(uint64_t)y.c, M, 1, 1};
+            uint64_t str[3] = {cs, cs * M, cs * M};
+            return encode_map(&maps[0], dt, yb, 4, dims, str, box, sw);
+        }
+        uint64_t dims[4] = {(uint64_t)y.c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+        uint64_t str[3] = {cs, cs * Wo, cs * Wo * Ho};
+        return encode_map(&maps[0], dt, yb, 4, dims, str, box, sw);
+    }
+    const uint64_t W2 = 2ull * Wo, H2 = 2ull * Ho;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+            uint64_t dims[4] = {(uint64_t)y.c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+            uint64_t str[3] = {2 * cs, 2 * cs * W2, cs * W2 * H2};
+            if (!encode_map(&maps[dy * 2 + dx], dt, yb + ((size_t)dy * W2 + dx) * cs, 4, dims, str, box, sw)) return false;
+        }
+    return true;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
 }
 
 int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
@@ -349,6 +514,10 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     const int up = a->upsample2x ? 2 : 1;
     YL_CHECK(y.n == x.n && y.h == Ho * up && y.w == Wo * up, YL_ERR_ARG,
              "conv output dims mismatch: got (%d,%d,%d) expected (%d,%d,%d)", y.n, y.h, y.w, x.n, Ho * up, Wo * up);
+    if (a->y_up.data)
+        YL_CHECK(a->y_up.n == x.n && a->y_up.h == 2 * Ho && a->y_up.w == 2 * Wo, YL_ERR_ARG,
+                 "y_up dims mismatch: got (%d,%d,%d) expected (%d,%d,%d)", a->y_up.n, a->y_up.h, a->y_up.w, x.n, 2 * Ho,
+                 2 * Wo);
 
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
@@ -358,19 +527,59 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     p.ci_pad = a->ci_pad;
     p.kblk = x.c >= 64 ? 64 : (x.c >= 32 ? 32 : 16);
     p.cin_blocks = ceil_div(x.c, p.kblk);
-    const CUtensorMapSwizzle sw = p.kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                               : (p.kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = swizzle_for_bytes(p.kblk * 2);
+    const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 
     // N tiling
     const int co16 = ceil_div(y.c, 16) * 16;
     const int n_tiles = ceil_div(co16, 256);
     p.co_tile = ceil_div(ceil_div(co16, n_tiles), 16) * 16;
 
+    // halo-patch mode: 3x3 stride-1 convs on thin inputs are L2->SM bound when every tap is fetched separately
+    // (9 narrow TMA boxes per tile); fetch the (TH+2) x (TW+2) patch once instead and slide the A descriptor
+    bool patch = false;
+    if (a->k == 3 && a->stride == 1 && x.c <= 64 && n_tiles == 1 && env_int("YL_PATCH", 1)) {
+        const int kb = env_int("YL_PATCH_K64", 0) ? 64 : p.kblk;
+        const double eff = (double)Ho * Wo / ((double)ceil_div(Wo, 8) * 8 * ceil_div(Ho, 16) * 16);
+        if (9 * p.co_tile * kb * 2 <= 40 * 1024 && eff >= 0.6) {
+            patch = true;
+            p.kblk = kb;
+            p.cin_blocks = 1;
+        }
+    }
+    const CUtensorMapSwizzle swp = swizzle_for_bytes(p.kblk * 2);
+
     // M tiling + activation tensor maps
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(x.data) + x.coff;
     const uint64_t es = 2;
-    const bool flat = (a->k == 1 && a->stride == 1 && !a->upsample2x);
-    if (flat) {
+    const bool flat = (a->k == 1 && a->stride == 1 && !a->upsample2x && !a->y_up.data);
+    if (patch) {
+        p.patch = 1;
+        p.patch_pw = env_int("YL_PATCH_PITCH", 10);
+        p.patch_bo = env_int("YL_PATCH_BO", 0);  // measured: the swizzle XOR uses absolute smem address bits
+        YL_CHECK(p.patch_pw >= 10 && p.patch_pw <= 16, YL_ERR_ARG, "YL_PATCH_PITCH must be in [10, 16]");
+        p.Ho = Ho;
+        p.Wo = Wo;
+        p.Nimg = x.n;
+        p.TW = 8;
+        p.TH = 16;
+        p.TN = 1;
+        p.tiles_w = ceil_div(Wo, 8);
+        p.tiles_h = ceil_div(Ho, 16);
+        p.tiles_n = x.n;
+        uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.patch_pw, 18u, 1u};
+        uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
+        uint64_t str[3] = {(uint64_t)x.cstride * es, (uint64_t)x.cstride * es * x.w,
+                           (uint64_t)x.cstride * es * x.w * x.h};
+        if (!encode_map(&p.tmA[0], bf, xb, 4, dims, str, box, swp)) return YL_ERR_CUDA;
+        // weights [co_pad][9][ci_pad] viewed as {ci, co, tap}
+        const uint64_t K = 9ull * a->ci_pad;
+        uint64_t wd[3] = {(uint64_t)a->ci_pad, (uint64_t)a->co_pad, 9};
+        uint64_t ws[2] = {K * es, (uint64_t)a->ci_pad * es};
+        uint32_t wb[3] = {(uint32_t)p.kblk, (uint32_t)p.co_tile, 9u};
+        if (!encode_map(&p.tmW3, bf, const_cast<void*>(a->w), 3, wd, ws, wb, swp)) return YL_ERR_CUDA;
+        p.tmB = p.tmW3;  // (prefetched by the producer; unused otherwise)
+    } else if (flat) {
         const uint64_t M = (uint64_t)x.n * x.h * x.w;
         YL_CHECK(M < (1ull << 31), YL_ERR_ARG, "too many pixels");
         p.Ho = 1;
@@ -385,7 +594,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)x.c, M, 1, 1};
         uint64_t str[3] = {(uint64_t)x.cstride * es, (uint64_t)x.cstride * es * M, (uint64_t)x.cstride * es * M};
         uint32_t box[4] = {(uint32_t)p.kblk, 128, 1, 1};
-        if (!encode_map(&p.tmA[0], xb, 4, dims, str, box, sw)) return YL_ERR_CUDA;
+        if (!encode_map(&p.tmA[0], bf, xb, 4, dims, str, box, sw)) return YL_ERR_CUDA;
     } else {
         p.Ho = Ho;
         p.Wo = Wo;
@@ -399,7 +608,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
             uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
             uint64_t str[3] = {(uint64_t)x.cstride * es, (uint64_t)x.cstride * es * x.w,
                                (uint64_t)x.cstride * es * x.w * x.h};
-            if (!encode_map(&p.tmA[0], xb, 4, dims, str, box, sw)) return YL_ERR_CUDA;
+            if (!encode_map(&p.tmA[0], bf, xb, 4, dims, str, box, sw)) return YL_ERR_CUDA;
         } else {
             for (int ph = 0; ph < 2; ++ph)
                 for (int pw = 0; pw < 2; ++pw) {
@@ -407,52 +616,85 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
                     uint64_t str[3] = {(uint64_t)x.cstride * es * 2, (uint64_t)x.cstride * es * x.w * 2,
                                        (uint64_t)x.cstride * es * x.w * x.h};
                     __nv_bfloat16* b = xb + ((size_t)ph * x.w + pw) * x.cstride;
-                    if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box, sw)) return YL_ERR_CUDA;
+                    if (!encode_map(&p.tmA[ph * 2 + pw], bf, b, 4, dims, str, box, sw)) return YL_ERR_CUDA;
                 }
         }
     }
     // weights: [co_pad][k*k*ci_pad] bf16
-    {
+    if (!patch) {
         const uint64_t K = (uint64_t)a->k * a->k * a->ci_pad;
         uint64_t dims[2] = {K, (uint64_t)a->co_pad};
         uint64_t str[1] = {K * es};
         uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.co_tile};
-        if (!encode_map(&p.tmB, const_cast<void*>(a->w), 2, dims, str, box, sw)) return YL_ERR_CUDA;
+        if (!encode_map(&p.tmB, bf, const_cast<void*>(a->w), 2, dims, str, box, sw)) return YL_ERR_CUDA;
+    }
+
+    // epilogue: chunk width, staging tile and destination tensor maps
+    p.y_f32 = (y.dtype == YL_F32);
+    const int oes = p.y_f32 ? 4 : 2;
+    p.cw = p.co_tile >= 32 ? 32 : 16;
+    p.nchunks = ceil_div(p.co_tile, p.cw);
+    p.acc_stride = p.nchunks * p.cw;
+    p.stg_row_bytes = p.cw * oes;
+    p.stg_bytes = 128u * (uint32_t)p.stg_row_bytes;  // multiple of 1024 for every (cw, dtype) except 16 x bf16
+    if (p.stg_bytes < 1024u) p.stg_bytes = 1024u;
+    p.stg_bytes = (p.stg_bytes + 1023u) & ~1023u;
+    {
+        const CUtensorMapSwizzle osw = swizzle_for_bytes(p.stg_row_bytes);
+        uint32_t obox[4] = {(uint32_t)p.cw, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        if (a->upsample2x) {
+            if (!encode_out_maps(&p.tmY[1], y, Ho, Wo, x.n, false, true, obox, osw)) return YL_ERR_CUDA;
+            p.y_map_first = 1;
+            p.y_map_last = 5;
+        } else {
+            if (!encode_out_maps(&p.tmY[0], y, Ho, Wo, x.n, flat, false, obox, osw)) return YL_ERR_CUDA;
+            p.y_map_first = 0;
+            p.y_map_last = 1;
+            if (a->y_up.data) {
+                if (!encode_out_maps(&p.tmY[1], a->y_up, Ho, Wo, x.n, false, true, obox, osw)) return YL_ERR_CUDA;
+                p.y_map_last = 5;
+            }
+        }
     }
 
     p.a_bytes = 128u * p.kblk * 2u;
     p.b_bytes = ((uint32_t)p.co_tile * p.kblk * 2u + 1023u) & ~1023u;
     p.tx_bytes = (uint32_t)(p.TW * p.TH * p.TN) * p.kblk * 2u + (uint32_t)p.co_tile * p.kblk * 2u;
+    if (patch) {
+        p.tx_bytes = (uint32_t)p.patch_pw * 18u * p.kblk * 2u;
+        p.a_bytes = (p.tx_bytes + 1023u) & ~1023u;
+        p.w_bytes = 9u * p.co_tile * p.kblk * 2u;
+        p.b_bytes = (p.w_bytes + 1023u) & ~1023u;
+    }
     p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.n_tiles = n_tiles;
     p.total_tiles = p.m_tiles * n_tiles;
-    // two accumulator stages whenever they fit the 512 TMEM columns; two CTAs per SM when TMEM and smem allow
-    p.acc_stages = (2 * p.co_tile <= 512) ? 2 : 1;
+    // two accumulator stages (one per epilogue group); two CTAs per SM when TMEM and smem allow
     uint32_t cols = 32;
-    while ((int)cols < p.acc_stages * p.co_tile) cols <<= 1;
+    while ((int)cols < 2 * p.acc_stride) cols <<= 1;
+    YL_CHECK(cols <= 512, YL_ERR_UNSUPPORTED, "accumulator needs %u TMEM columns", cols);
     p.tmem_cols = cols;
     const int ctas_per_sm = (cols <= 256) ? 2 : 1;
-    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    const uint32_t budget = (uint32_t)(ctas_per_sm == 2 ? 108 * 1024 : 200 * 1024);
+    const int nbias = n_tiles * p.co_tile + 32;
+    const size_t fixed = 1024 + 2 * (size_t)p.stg_bytes + (size_t)((nbias + 3) & ~3) * 4 + 16;
+    const uint32_t stage_bytes = patch ? p.a_bytes : p.a_bytes + p.b_bytes;
+    const size_t fixed_b = patch ? p.b_bytes : 0;
+    const size_t budget = (size_t)(ctas_per_sm == 2 ? 112 * 1024 : 224 * 1024) - fixed - fixed_b - 16 * 24 - 64;
     int stages = (int)(budget / stage_bytes);
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+    const size_t smem = fixed + fixed_b + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 16;
     YL_CHECK((int)smem <= g_max_dyn_smem, YL_ERR_UNSUPPORTED, "conv tile needs %zu B smem (max %d)", smem,
              g_max_dyn_smem);
 
-    p.y = y.data;
-    p.y_cstride = y.cstride;
-    p.y_coff = y.coff;
-    p.y_c = y.c;
-    p.y_f32 = (y.dtype == YL_F32);
     p.bias = a->bias;
+    p.n_bias = a->co_pad;
     p.act = a->act;
     p.res = reinterpret_cast<const __nv_bfloat16*>(a->res.data);
     p.res_cstride = a->res.cstride;
     p.res_coff = a->res.coff;
-    p.upsample = a->upsample2x ? 1 : 0;
+    p.res_c = a->res.c;
 
     int grid = g_num_sms * ctas_per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;

@@ -45,6 +45,7 @@ class ConvArgs(C.Structure):
         ("x", Tensor),
         ("y", Tensor),
         ("res", Tensor),
+        ("y_up", Tensor),
         ("w", C.c_void_p),
         ("bias", C.c_void_p),
         ("k", C.c_int32),

@@ -106,10 +106,11 @@ def pack_conv(weight: torch.Tensor, bn=None, conv_bias=None, device=None) -> Pac
 
 
 def conv_args(x: View, y: View, pc: PackedConv, stride=1, act=True, res: View | None = None, upsample=False,
-              impl=_C.IMPL_AUTO) -> _C.ConvArgs:
+              impl=_C.IMPL_AUTO, y_up: View | None = None) -> _C.ConvArgs:
     a = _C.ConvArgs()
     a.x, a.y = x.ct(), y.ct()
     a.res = res.ct() if res is not None else _C.null_tensor()
+    a.y_up = y_up.ct() if y_up is not None else _C.null_tensor()
     a.w, a.bias = pc.w.data_ptr(), pc.bias.data_ptr()
     a.k, a.stride, a.ci_pad, a.co_pad = pc.k, stride, pc.ci_pad, pc.co_pad
     a.act = _C.ACT_SILU if act else _C.ACT_NONE
@@ -118,7 +119,8 @@ def conv_args(x: View, y: View, pc: PackedConv, stride=1, act=True, res: View | 
     return a
 
 
-def conv(x: View, y: View, pc: PackedConv, stride=1, act=True, res=None, upsample=False, impl=_C.IMPL_AUTO):
+def conv(x: View, y: View, pc: PackedConv, stride=1, act=True, res=None, upsample=False, impl=_C.IMPL_AUTO,
+         y_up=None):
     lib = _C.load()
     if pc.depthwise:
         assert stride == 1 and pc.k == 3 and not upsample, "depthwise path is 3x3 stride 1"
@@ -126,7 +128,7 @@ def conv(x: View, y: View, pc: PackedConv, stride=1, act=True, res=None, upsampl
         _C.check(lib.yl_dwconv3x3(C.byref(x.ct()), C.byref(y.ct()), pc.w.data_ptr(), pc.bias.data_ptr(), int(act),
                                   addp, _C.stream_ptr()), "yl_dwconv3x3")
         return
-    a = conv_args(x, y, pc, stride, act, res, upsample, impl)
+    a = conv_args(x, y, pc, stride, act, res, upsample, impl, y_up)
     _C.check(lib.yl_conv_bn_act(C.byref(a), _C.stream_ptr()), "yl_conv_bn_act")
 
 

@@ -29,6 +29,16 @@ class Dest:
         return v
 
 
+class DualDest:
+    """Two placements for one conv result: `primary` (None | View | Dest) at conv resolution and `up`
+    (None | View | Dest) receiving the nearest-2x replicated copy (nn.Upsample fused into the producer's TMA
+    store).  After emission `up_view` holds the upsampled View."""
+
+    def __init__(self, primary, up):
+        self.primary, self.up = primary, up
+        self.up_view: View | None = None
+
+
 class NchwInput:
     """The caller's NCHW fp32 batch, not yet converted.  A stem conv consumes it directly (fused ingest);
     anything else forces the NHWC bf16 materialisation."""
@@ -91,6 +101,10 @@ class Builder:
     def conv(self, x: View, pc: PackedConv, stride=1, act=True, out=None, res: View | None = None,
              upsample=False, out_dtype=torch.bfloat16, impl=_C.IMPL_AUTO) -> View:
         k = pc.k
+        dual = None
+        if isinstance(out, DualDest):
+            dual, out = out, out.primary
+            assert not pc.depthwise and not upsample and not isinstance(x, NchwInput)
         if isinstance(x, NchwInput):
             if (x.view is None and not self.calls and k == 3 and stride == 2 and x.c <= 4 and not pc.depthwise
                     and res is None and not upsample and out_dtype is torch.bfloat16
@@ -117,16 +131,19 @@ class Builder:
                        C.byref(rt) if rt is not None else None, keep=(xt, yt, rt, pc), kind="dwconv3x3",
                        bytes_=px * x.c * 2 * (2 + (res is not None)) + 9 * x.c * 2, flops=2 * 9 * px * x.c)
             return y
-        a = _ops.conv_args(x, y, pc, stride, act, res, upsample, impl)
+        y_up = None
+        if dual is not None:
+            y_up = dual.up_view = self._out(dual.up, x.n, 2 * ho, 2 * wo, pc.co, out_dtype)
+        a = _ops.conv_args(x, y, pc, stride, act, res, upsample, impl, y_up)
         opx = x.n * ho * wo
         esz = 4 if out_dtype is torch.float32 else 2
         tc = impl != _C.IMPL_DIRECT and bool(self.lib.yl_conv_tc_supported(C.byref(a)))
         self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc), kind="conv_tc" if tc else "conv_direct",
                    bytes_=x.n * x.h * x.w * x.c * 2 + opx * pc.co * esz * u * u + k * k * x.c * pc.co * 2
-                   + (opx * pc.co * 2 if res is not None else 0),
+                   + (opx * pc.co * 2 if res is not None else 0) + (4 * opx * pc.co * esz if y_up is not None else 0),
                    flops=2 * opx * pc.co * x.c * k * k,
                    desc=f"{x.c}->{pc.co} k{k}s{stride} {x.h}x{x.w}" + (" +res" if res is not None else "")
-                   + (" up2" if upsample else "") + (" f32" if esz == 4 else ""))
+                   + (" up2" if upsample else "") + (" +up2" if y_up is not None else "") + (" f32" if esz == 4 else ""))
         return y
 
     def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):

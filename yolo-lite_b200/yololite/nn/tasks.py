@@ -224,6 +224,21 @@ class BaseModel(YLModule):
 
             return _plan.Dest(resolve)
 
+        # nn.Upsample fused into its producer: when layer j ends in a dense conv, that conv's TMA store also
+        # writes the 2x2-replicated copy straight into the upsample's destination (usually a Concat slice)
+        n_uses = [0] * n_layers
+        for i in range(n_layers):
+            for j in srcs[i]:
+                if j >= 0:
+                    n_uses[j] += 1
+        fused_up = {}                    # producer layer j -> upsample layer u
+        for u, m in enumerate(layers):
+            if isinstance(m, nn.Upsample) and m.mode == "nearest" and float(m.scale_factor) == 2.0:
+                j = srcs[u][0]
+                if j >= 0 and isinstance(layers[j], (Conv, C2f, C3, SPPF, C2PSA)) and j not in fused_up:
+                    fused_up[j] = u
+        done_up = {}
+
         cur = x
         for i, m in enumerate(layers):
             inp = [ys[j] if j >= 0 else x for j in srcs[i]]
@@ -235,6 +250,14 @@ class BaseModel(YLModule):
                     cur = View(buf.buf, buf.coff, sum(chans))   # sources already live in the buffer
                 else:
                     cur = m._emit(g, inp, out=dest_for(i))
+            elif i in done_up:
+                cur = done_up[i]
+            elif i in fused_up:
+                u = fused_up[i]
+                dd = _plan.DualDest(dest_for(i), dest_for(u))
+                cur = emit_any(g, m, inp[0], out=dd)
+                assert dd.up_view is not None, f"layer {i}: producer did not honour the fused upsample"
+                done_up[u] = dd.up_view
             else:
                 cur = emit_any(g, m, inp[0], out=dest_for(i))
             ys[i] = cur
