@@ -2,9 +2,13 @@
 // Tokens are the H*W pixels; q|k|v of a head are 2*kd+hd contiguous channels of the NHWC qkv tensor, so every
 // operand row is a contiguous run (64 B q/k, 128 B v).
 //
-// v0 (this file): flash-style streaming softmax on CUDA cores — one thread per query, K/V tiles of 64 keys
-// staged in shared memory and read as warp-wide broadcasts, fp32 accumulation, no N x N matrix in HBM.
-// The tcgen05 version (S in TMEM) replaces it once the conv path is tuned; attention is <1 % of the FLOPs.
+// Flash-style fused kernel on the tensor cores: one CTA = 64 queries of one (image, head), 4 warps x 16 query
+// rows.  Key/value tiles of 64 tokens are staged in padded shared memory (conflict-free ldmatrix); S = Q K^T
+// and O += P V run as mma.sync.m16n8k16 bf16 with fp32 accumulators held in registers (S never leaves the
+// register file: the accumulator fragment of S is re-packed in place as the A fragment of P), online softmax
+// in the log2 domain (one MUFU.EX2 per score), no N x N matrix in HBM.  The whole problem is 61 MFLOP and
+// 0.3 MB per image (N = 400 tokens, 2-4 heads), i.e. latency-bound: register-resident mma.sync tiles beat a
+// TMEM round trip here, which is why this kernel does not use tcgen05 (the convolutions do).
 #include "common.cuh"
 
 namespace yl {
@@ -20,98 +24,146 @@ struct AttnParams {
     float scale;
 };
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                 "{%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 template <int KD, int HD>
 __global__ void __launch_bounds__(128) psa_attention_kernel(const AttnParams p) {
-    constexpr int KT = 64;                     // keys per shared-memory tile
-    constexpr int SUB = 16;                    // keys per online-softmax step
-    __shared__ __align__(16) uint4 sK[KT * KD / 8];
-    __shared__ __align__(16) uint4 sV[KT * HD / 8];
+    constexpr int QT = 64, KT = 64;
+    constexpr int KP = KD + 8, VP = HD + 8;  // padded pitches (elements): 16-B rows land on distinct banks
+    __shared__ __align__(16) __nv_bfloat16 sQ[QT * KP];
+    __shared__ __align__(16) __nv_bfloat16 sK[KT * KP];
+    __shared__ __align__(16) __nv_bfloat16 sV[KT * VP];
     const int head = blockIdx.y, b = blockIdx.z;
-    const int i = blockIdx.x * 128 + threadIdx.x;  // query token
-    const int iq = min(i, p.N - 1);
-    const int hc = head * (2 * KD + HD);
-    const __nv_bfloat16* base = p.qkv + (long long)b * p.N * p.q_cstride + p.q_coff + hc;
+    const int q0 = blockIdx.x * QT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* base = p.qkv + (long long)b * p.N * p.q_cstride + p.q_coff + head * (2 * KD + HD);
 
-    float q[KD];
-    {
-        const uint4* qp = reinterpret_cast<const uint4*>(base + (long long)iq * p.q_cstride);
-#pragma unroll
-        for (int v = 0; v < KD / 8; ++v) {
-            const uint4 t = __ldg(qp + v);
-            q[v * 8 + 0] = bf16lo_f(t.x) * p.scale; q[v * 8 + 1] = bf16hi_f(t.x) * p.scale;
-            q[v * 8 + 2] = bf16lo_f(t.y) * p.scale; q[v * 8 + 3] = bf16hi_f(t.y) * p.scale;
-            q[v * 8 + 4] = bf16lo_f(t.z) * p.scale; q[v * 8 + 5] = bf16hi_f(t.z) * p.scale;
-            q[v * 8 + 6] = bf16lo_f(t.w) * p.scale; q[v * 8 + 7] = bf16hi_f(t.w) * p.scale;
-        }
+    // ---- Q tile -> smem -> A fragments (2 k-steps of 16)
+    for (int e = tid; e < QT * (KD / 8); e += 128) {
+        const int r = e / (KD / 8), v = e - r * (KD / 8);
+        const int qi = min(q0 + r, p.N - 1);
+        *reinterpret_cast<uint4*>(&sQ[r * KP + v * 8]) =
+            __ldg(reinterpret_cast<const uint4*>(base + (long long)qi * p.q_cstride) + v);
     }
-    float o[HD];
+    __syncthreads();
+    uint32_t qa[KD / 16][4];
 #pragma unroll
-    for (int c = 0; c < HD; ++c) o[c] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    for (int ks = 0; ks < KD / 16; ++ks) {
+        const int row = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int col = ks * 16 + 8 * (lane >> 4);
+        ldsm_x4(qa[ks], smem_u32(&sQ[row * KP + col]));
+    }
+
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // rows g and g+8 of this warp's 16 queries
+    const float sl2 = p.scale * 1.4426950408889634f;
 
     for (int j0 = 0; j0 < p.N; j0 += KT) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < KT * (KD / 8); e += 128) {
-            const int j = e / (KD / 8), v = e - j * (KD / 8);
-            const int jj = min(j0 + j, p.N - 1);
-            sK[e] = __ldg(reinterpret_cast<const uint4*>(base + (long long)jj * p.q_cstride + KD) + v);
+        __syncthreads();  // previous tile fully consumed
+        for (int e = tid; e < KT * (KD / 8); e += 128) {
+            const int r = e / (KD / 8), v = e - r * (KD / 8);
+            const int kj = min(j0 + r, p.N - 1);
+            *reinterpret_cast<uint4*>(&sK[r * KP + v * 8]) =
+                __ldg(reinterpret_cast<const uint4*>(base + (long long)kj * p.q_cstride + KD) + v);
         }
-        for (int e = threadIdx.x; e < KT * (HD / 8); e += 128) {
-            const int j = e / (HD / 8), v = e - j * (HD / 8);
-            const int jj = min(j0 + j, p.N - 1);
-            sV[e] = __ldg(reinterpret_cast<const uint4*>(base + (long long)jj * p.q_cstride + 2 * KD) + v);
+        for (int e = tid; e < KT * (HD / 8); e += 128) {
+            const int r = e / (HD / 8), v = e - r * (HD / 8);
+            const int kj = min(j0 + r, p.N - 1);
+            *reinterpret_cast<uint4*>(&sV[r * VP + v * 8]) =
+                __ldg(reinterpret_cast<const uint4*>(base + (long long)kj * p.q_cstride + 2 * KD) + v);
         }
         __syncthreads();
-        const int kmax = min(KT, p.N - j0);
-        for (int s0 = 0; s0 < kmax; s0 += SUB) {
-            float s[SUB];
-            float mx = m;
+
+        // ---- S = Q K^T : 16 queries x 64 keys per warp
+        float sc[KT / 8][4];
 #pragma unroll
-            for (int jj = 0; jj < SUB; ++jj) {
-                float acc = 0.f;
+        for (int nt = 0; nt < KT / 8; ++nt) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            uint32_t kb[4];  // (k 0-7, 8-15, 16-23, 24-31) of keys nt*8..nt*8+7
+            ldsm_x4(kb, smem_u32(&sK[(nt * 8 + (lane & 7)) * KP + 8 * (lane >> 3)]));
+            mma_bf16_16816(sc[nt], qa[0], kb[0], kb[1]);
+            mma_bf16_16816(sc[nt], qa[1], kb[2], kb[3]);
+        }
+        // ---- online softmax (log2 domain), rows g (regs 0,1) and g+8 (regs 2,3)
+        float mx0 = m0, mx1 = m1;
 #pragma unroll
-                for (int v = 0; v < KD / 8; ++v) {
-                    const uint4 t = sK[(s0 + jj) * (KD / 8) + v];
-                    acc = fmaf(q[v * 8 + 0], bf16lo_f(t.x), acc); acc = fmaf(q[v * 8 + 1], bf16hi_f(t.x), acc);
-                    acc = fmaf(q[v * 8 + 2], bf16lo_f(t.y), acc); acc = fmaf(q[v * 8 + 3], bf16hi_f(t.y), acc);
-                    acc = fmaf(q[v * 8 + 4], bf16lo_f(t.z), acc); acc = fmaf(q[v * 8 + 5], bf16hi_f(t.z), acc);
-                    acc = fmaf(q[v * 8 + 6], bf16lo_f(t.w), acc); acc = fmaf(q[v * 8 + 7], bf16hi_f(t.w), acc);
-                }
-                s[jj] = (s0 + jj < kmax) ? acc : -INFINITY;
-                mx = fmaxf(mx, s[jj]);
-            }
-            const float corr = __expf(m - mx);  // m = -inf on the first step -> 0
-            l *= corr;
+        for (int nt = 0; nt < KT / 8; ++nt) {
+            const int key = j0 + nt * 8 + 2 * t;
+            sc[nt][0] = key < p.N ? sc[nt][0] * sl2 : -INFINITY;
+            sc[nt][1] = key + 1 < p.N ? sc[nt][1] * sl2 : -INFINITY;
+            sc[nt][2] = key < p.N ? sc[nt][2] * sl2 : -INFINITY;
+            sc[nt][3] = key + 1 < p.N ? sc[nt][3] * sl2 : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);  // first tile: exp2(-inf) = 0
+        m0 = mx0;
+        m1 = mx1;
+        l0 *= c0;
+        l1 *= c1;
 #pragma unroll
-            for (int c = 0; c < HD; ++c) o[c] *= corr;
-            m = mx;
+        for (int i = 0; i < HD / 8; ++i) {
+            o[i][0] *= c0; o[i][1] *= c0;
+            o[i][2] *= c1; o[i][3] *= c1;
+        }
+        uint32_t pa[KT / 16][4];  // P as A fragments: k-step kk covers keys 16kk..16kk+15
 #pragma unroll
-            for (int jj = 0; jj < SUB; ++jj) {
-                const float pj = __expf(s[jj] - m);
-                l += pj;
+        for (int nt = 0; nt < KT / 8; ++nt) {
+            const float p0 = exp2f(sc[nt][0] - m0), p1 = exp2f(sc[nt][1] - m0);
+            const float p2 = exp2f(sc[nt][2] - m1), p3 = exp2f(sc[nt][3] - m1);
+            l0 += p0 + p1;
+            l1 += p2 + p3;
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        // ---- O += P V
 #pragma unroll
-                for (int v = 0; v < HD / 8; ++v) {
-                    const uint4 t = sV[(s0 + jj) * (HD / 8) + v];
-                    o[v * 8 + 0] = fmaf(pj, bf16lo_f(t.x), o[v * 8 + 0]); o[v * 8 + 1] = fmaf(pj, bf16hi_f(t.x), o[v * 8 + 1]);
-                    o[v * 8 + 2] = fmaf(pj, bf16lo_f(t.y), o[v * 8 + 2]); o[v * 8 + 3] = fmaf(pj, bf16hi_f(t.y), o[v * 8 + 3]);
-                    o[v * 8 + 4] = fmaf(pj, bf16lo_f(t.z), o[v * 8 + 4]); o[v * 8 + 5] = fmaf(pj, bf16hi_f(t.z), o[v * 8 + 5]);
-                    o[v * 8 + 6] = fmaf(pj, bf16lo_f(t.w), o[v * 8 + 6]); o[v * 8 + 7] = fmaf(pj, bf16hi_f(t.w), o[v * 8 + 7]);
-                }
+        for (int kk = 0; kk < KT / 16; ++kk) {
+#pragma unroll
+            for (int np = 0; np < HD / 16; ++np) {
+                uint32_t vb[4];  // b0,b1 of channel tile 2np, b0,b1 of channel tile 2np+1
+                const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+                const int ch = np * 16 + 8 * (lane >> 4);
+                ldsm_x4_trans(vb, smem_u32(&sV[key * VP + ch]));
+                mma_bf16_16816(o[2 * np], pa[kk], vb[0], vb[1]);
+                mma_bf16_16816(o[2 * np + 1], pa[kk], vb[2], vb[3]);
             }
         }
     }
-    if (i < p.N) {
-        const float inv = 1.f / l;
-        uint4* op = reinterpret_cast<uint4*>(p.out + ((long long)b * p.N + i) * p.o_cstride + p.o_coff + head * HD);
+    // ---- normalise and store (quad-reduced row sums)
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    __nv_bfloat16* ob = p.out + (long long)b * p.N * p.o_cstride + p.o_coff + head * HD + 2 * t;
 #pragma unroll
-        for (int v = 0; v < HD / 8; ++v) {
-            uint4 t;
-            t.x = pack_bf16x2(o[v * 8 + 0] * inv, o[v * 8 + 1] * inv);
-            t.y = pack_bf16x2(o[v * 8 + 2] * inv, o[v * 8 + 3] * inv);
-            t.z = pack_bf16x2(o[v * 8 + 4] * inv, o[v * 8 + 5] * inv);
-            t.w = pack_bf16x2(o[v * 8 + 6] * inv, o[v * 8 + 7] * inv);
-            op[v] = t;
-        }
+    for (int i = 0; i < HD / 8; ++i) {
+        if (r0 < p.N)
+            *reinterpret_cast<uint32_t*>(ob + (long long)r0 * p.o_cstride + i * 8) = pack_bf16x2(o[i][0] * i0, o[i][1] * i0);
+        if (r1 < p.N)
+            *reinterpret_cast<uint32_t*>(ob + (long long)r1 * p.o_cstride + i * 8) = pack_bf16x2(o[i][2] * i1, o[i][3] * i1);
     }
 }
 
@@ -139,7 +191,7 @@ extern "C" int yl_psa_attention(const yl_tensor* qkv, const yl_tensor* out, int 
     p.o_coff = out->coff;
     p.N = qkv->h * qkv->w;
     p.scale = scale;
-    dim3 grid((unsigned)yl::ceil_div(p.N, 128), (unsigned)heads, (unsigned)qkv->n);
+    dim3 grid((unsigned)yl::ceil_div(p.N, 64), (unsigned)heads, (unsigned)qkv->n);
     yl::psa_attention_kernel<32, 64><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
     YL_LAUNCH_OK("psa_attention_kernel");
     return YL_OK;

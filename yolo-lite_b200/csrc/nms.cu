@@ -202,6 +202,38 @@ __device__ __forceinline__ void fetch_box(const SelParams& p, int b, unsigned lo
     *area = __fmul_rn(__fsub_rn(off->z, off->x), __fsub_rn(off->w, off->y));
 }
 
+// ascending keys == descending score: in-place bitonic sort of skeys[0..P), P a power of two
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* skeys, int P, int tid) {
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += kSelThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = skeys[i], y = skeys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        skeys[i] = y;
+                        skeys[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// Coarse score bin of a key, monotone in the key order (smaller key = higher score = smaller bin).  Used to cut
+// a large candidate list into rounds of ~kRoundTarget best candidates without sorting everything: with
+// max_det = 300 the greedy scan almost always finishes inside the first round.
+constexpr int kBins = 4096;
+constexpr int kRoundTarget = 1024;
+constexpr int kBinMax = 4096;                     // a single bin larger than this falls back to radix select
+constexpr int kDirectSort = 2048;                 // at most this many candidates: sort them all directly
+__device__ __forceinline__ int key_bin(unsigned long long k) {
+    const float t = desc_to_score((uint32_t)(k >> 32)) * (float)kBins;
+    const int b = t >= (float)(kBins - 1) ? (kBins - 1) : (t > 0.f ? (int)t : 0);
+    return (kBins - 1) - b;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -231,11 +263,55 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
     int nk = 0;          // kept so far (uniform across the block)
     int processed = 0;   // candidates consumed in sorted order
     unsigned long long lo = 0;  // keys <= lo are already consumed (radix rounds)
-    const bool single_round = n <= kSortCap;
+    const bool single_round = n <= kDirectSort;
+    // bin mode: cumulative histogram of the coarse score bins (lives in the tail of the key buffer)
+    uint32_t* cum = reinterpret_cast<uint32_t*>(skeys + (kSortCap - kBins / 2));
+    bool use_bins = false;
+    int bpos = 0;  // bins < bpos are consumed
+    if (!single_round) {
+        for (int i = tid; i < kBins; i += kSelThreads) cum[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kSelThreads) atomicAdd(&cum[key_bin(gkeys[i])], 1u);
+        __syncthreads();
+        // block-wide inclusive scan, kBins / kSelThreads (= 4) bins per thread
+        constexpr int PER = kBins / kSelThreads;
+        uint32_t v[PER], tsum = 0, big = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            v[i] = cum[tid * PER + i];
+            big |= (v[i] > (uint32_t)kBinMax);
+            tsum += v[i];
+        }
+        uint32_t incl = tsum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) hist[warp] = incl;
+        use_bins = !__syncthreads_or((int)big);
+        if (warp == 0) {
+            const uint32_t w = hist[lane];
+            uint32_t wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            hist[lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t run = hist[warp] + incl - tsum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            run += v[i];
+            cum[tid * PER + i] = run;
+        }
+        __syncthreads();
+    }
 
     while (processed < n_proc && nk < p.max_det) {
         int m = n_proc - processed;
         if (m > kSortCap) m = kSortCap;
+        int consumed = m;  // candidates this round removes from the unprocessed set
         // ---------------- stage the next m keys (ascending) into shared memory
         if (single_round) {
             for (int i = tid; i < n; i += kSelThreads) skeys[i] = gkeys[i];
@@ -243,21 +319,49 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             while (P < n) P <<= 1;
             for (int i = n + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
             __syncthreads();
-            for (int k = 2; k <= P; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < P; i += kSelThreads) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const unsigned long long x = skeys[i], y = skeys[ixj];
-                            const bool up = (i & k) == 0;
-                            if ((x > y) == up) {
-                                skeys[i] = y;
-                                skeys[ixj] = x;
-                            }
-                        }
-                    }
-                    __syncthreads();
+            block_bitonic_sort(skeys, P, tid);
+        } else if (use_bins) {
+            // the best ~kRoundTarget unconsumed candidates: bins [bpos, e)
+            if (tid == 0) {
+                const uint32_t base = bpos ? cum[bpos - 1] : 0u;
+                int lo_b = bpos, hi_b = kBins - 1;  // smallest e-1 with cum[e-1] - base >= target (or last bin)
+                while (lo_b < hi_b) {
+                    const int mid = (lo_b + hi_b) >> 1;
+                    if (cum[mid] - base >= (uint32_t)kRoundTarget) hi_b = mid; else lo_b = mid + 1;
                 }
+                misc[0] = lo_b + 1;
+                misc[1] = (int)(cum[lo_b] - base);
+                misc[2] = 0;
+            }
+            __syncthreads();
+            const int e = misc[0];
+            const int mr = misc[1];  // <= kRoundTarget - 1 + kBinMax keys fall into this round
+            for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+                const int i = i0 + tid;
+                unsigned long long k = 0;
+                bool take = false;
+                if (i < n) {
+                    k = gkeys[i];
+                    const int kb = key_bin(k);
+                    take = kb >= bpos && kb < e;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, take);
+                if (bal) {
+                    int pos0 = 0;
+                    if (lane == 0) pos0 = atomicAdd(&misc[2], __popc(bal));
+                    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                    if (take) skeys[pos0 + __popc(bal & ((1u << lane) - 1u))] = k;
+                }
+            }
+            __syncthreads();
+            int P = 32;
+            while (P < mr) P <<= 1;
+            for (int i = mr + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
+            __syncthreads();
+            block_bitonic_sort(skeys, P, tid);
+            bpos = e;
+            consumed = mr;
+            m = mr < (n_proc - processed) ? mr : (n_proc - processed);  // max_nms cut inside the round
         } else {
             // radix select: T = m-th smallest key among keys > lo (8 passes of 8 bits, MSD first)
             unsigned long long prefix = 0, pmask = 0;
@@ -300,21 +404,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             while (P < m) P <<= 1;
             for (int i = m + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
             __syncthreads();
-            for (int k = 2; k <= P; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < P; i += kSelThreads) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const unsigned long long x = skeys[i], y = skeys[ixj];
-                            const bool up = (i & k) == 0;
-                            if ((x > y) == up) {
-                                skeys[i] = y;
-                                skeys[ixj] = x;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
+            block_bitonic_sort(skeys, P, tid);
             lo = T;
         }
 
@@ -416,7 +506,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             nk = misc[4];
             __syncthreads();
         }
-        processed += m;
+        processed += consumed;
     }
 
     // ---------------- emit
