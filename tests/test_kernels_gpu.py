@@ -167,6 +167,40 @@ def test_conv_stem_direct(ops):
     np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("case", [
+    # ci, co, n, h, w, act, y_pad, tag
+    (3, 16, 2, 64, 64, True, 0, "rgb_co16"),
+    (3, 32, 1, 96, 160, True, 32, "rgb_co32_slice_wide"),
+    (3, 64, 2, 36, 70, True, 0, "rgb_co64_ragged_w"),
+    (2, 16, 1, 34, 38, False, 0, "two_channel_noact"),
+    (4, 48, 1, 40, 72, True, 0, "rgba_co48_k36"),
+    (3, 16, 1, 35, 67, True, 0, "odd_hw"),
+], ids=lambda c: c[-1])
+def test_stem_conv_fused_ingest(ops, case):
+    """yl_stem_conv (NCHW fp32 in, mma.sync im2col-in-registers) vs fp32 conv on bf16-rounded operands."""
+    ci, co, n, h, w, act, y_pad, tag = case
+    g = torch.Generator().manual_seed(zlib.crc32(tag.encode()) % 2**31)
+    x = torch.rand(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) * 0.4
+    bn = (torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g) * 0.1, torch.randn(co, generator=g) * 0.1,
+          torch.rand(co, generator=g) + 0.5, 1e-3)
+    pc = ops.pack_conv(wt, bn=bn)
+    scale = bn[0] / torch.sqrt(bn[3] + 1e-3)
+    ref = F.conv2d(bf16r(x), bf16r(wt * scale.view(-1, 1, 1, 1)), bn[1] - bn[2] * scale, 2, 1)
+    if act:
+        ref = F.silu(ref)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    yb = torch.full((n, ho, wo, co + y_pad), -3.0, dtype=torch.bfloat16, device="cuda")
+    yv = ops.View(yb, y_pad // 2, co)
+    ops.stem_conv(x.cuda(), yv, pc, act)
+    torch.cuda.synchronize()
+    got = yv.torch_nhwc().float().cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-2, atol=2e-2)
+    if y_pad:
+        rest = torch.cat([yb[..., : y_pad // 2], yb[..., y_pad // 2 + co:]], -1)
+        assert bool((rest == -3.0).all())
+
+
 def test_layout_roundtrip(ops):
     x = torch.randn(2, 144, 9, 13)
     v = ops.new_buffer(2, 9, 13, 160)
@@ -176,10 +210,12 @@ def test_layout_roundtrip(ops):
     np.testing.assert_array_equal(back.cpu().numpy(), bf16r(x).numpy())
 
 
-def test_dwconv3x3(ops):
+@pytest.mark.parametrize("shape", [(2, 80, 11, 13), (1, 64, 20, 20), (3, 128, 7, 4), (1, 8, 5, 1), (2, 256, 9, 18)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_dwconv3x3(ops, shape):
     g = torch.Generator().manual_seed(5)
-    c = 80
-    x = torch.randn(2, c, 11, 13, generator=g)
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, generator=g)
     wt = torch.randn(c, 1, 3, 3, generator=g) * 0.3
     bn = (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1, torch.randn(c, generator=g) * 0.1,
           torch.rand(c, generator=g) + 0.5, 1e-3)
@@ -188,7 +224,7 @@ def test_dwconv3x3(ops):
     scale = bn[0] / torch.sqrt(bn[3] + 1e-3)
     ref = F.silu(F.conv2d(bf16r(x), bf16r(wt * scale.view(-1, 1, 1, 1)), bn[1] - bn[2] * scale, 1, 1, 1, c))
     xv = ops.View(nhwc(x, c + 16, 8), 8, c)
-    yv = ops.new_buffer(2, 11, 13, c)
+    yv = ops.new_buffer(n, h, w, c)
     ops.conv(xv, yv, pc, 1, True)
     torch.cuda.synchronize()
     got = yv.torch_nhwc().float().cpu().permute(0, 3, 1, 2)

@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(128) psa_attention_kernel(const AttnParams p) 
     __shared__ __align__(16) __nv_bfloat16 sQ[QT * KP];
     __shared__ __align__(16) __nv_bfloat16 sK[KT * KP];
     __shared__ __align__(16) __nv_bfloat16 sV[KT * VP];
+    griddep_launch_dependents();
+    griddep_wait();
     const int head = blockIdx.y, b = blockIdx.z;
     const int q0 = blockIdx.x * QT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -192,7 +194,7 @@ extern "C" int yl_psa_attention(const yl_tensor* qkv, const yl_tensor* out, int 
     p.N = qkv->h * qkv->w;
     p.scale = scale;
     dim3 grid((unsigned)yl::ceil_div(p.N, 64), (unsigned)heads, (unsigned)qkv->n);
-    yl::psa_attention_kernel<32, 64><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    YL_CUDA(yl::launch_kernel(yl::psa_attention_kernel<32, 64>, grid, dim3(128), 0, (cudaStream_t)stream, p));
     YL_LAUNCH_OK("psa_attention_kernel");
     return YL_OK;
 }

@@ -2,6 +2,8 @@
 // stem and for shapes the tcgen05 path rejects, the depthwise 3x3, and the one-time BN fold + weight pack.
 // All are HBM/L2-bound: threads map to (pixel, 8-channel group) with channels innermost so every global
 // access is a contiguous 16-byte vector inside a pixel's channel run.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace yl {
@@ -164,63 +166,108 @@ struct DwParams {
     int N, H, W, C, act;
 };
 
+// One thread = a strip of P consecutive output pixels of one row x 8 channels.  The 3 x (P+2) input vectors
+// are each loaded once (4.5 loads per output for P = 4 instead of 9), the 9 x 8 weights live in registers as
+// fp32.  Consecutive threads take consecutive 8-channel groups, so a warp reads whole pixels (>= 128 B runs).
+template <int P>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
-    const int groups = p.C >> 3;
-    const long long total = (long long)p.N * p.H * p.W * groups;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    griddep_launch_dependents();
+    // 32-bit index math only (64-bit div/mod is a ~100-instruction software routine): blockIdx.y = image,
+    // the x index runs over (row, strip, channel group) of one image
+    const unsigned groups = (unsigned)p.C >> 3;
+    const unsigned strips = (unsigned)(p.W + P - 1) / P;
+    const unsigned per_image = (unsigned)p.H * strips * groups;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_image) return;
     const int g = (int)(idx % groups);
-    const long long pix = idx / groups;
-    const int w = (int)(pix % p.W);
-    const int h = (int)((pix / p.W) % p.H);
-    const int n = (int)(pix / ((long long)p.W * p.H));
+    unsigned t = idx / groups;
+    const int w0 = (int)(t % strips) * P;
+    const int h = (int)(t / strips);
+    const int n = blockIdx.y;
     const int c = g * 8;
 
-    float acc[8];
+    griddep_wait();  // weights / bias are constants; activations only from here on
+    // phase 1: every input vector of the 3 x (P+2) window in flight at once (clamped addresses, no branches:
+    // the kernel is latency-bound, so the loads must not be serialised behind bounds checks)
+    const long long row0 = ((long long)n * p.H + h) * p.W;
+    uint4 xv[3][P + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int hi = min(max(h + r - 1, 0), p.H - 1);
+        const __nv_bfloat16* xrow = p.x + ((long long)n * p.H + hi) * p.W * p.x_cstride + p.x_coff + c;
+#pragma unroll
+        for (int j = 0; j < P + 2; ++j) {
+            const int wi = min(max(w0 + j - 1, 0), p.W - 1);
+            xv[r][j] = __ldg(reinterpret_cast<const uint4*>(xrow + (long long)wi * p.x_cstride));
+        }
+    }
+    uint4 wv[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wv[tap] = __ldg(reinterpret_cast<const uint4*>(p.w + tap * p.C + c));
+    float acc[P][8];
     {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+#pragma unroll
+        for (int o = 0; o < P; ++o) {
+            acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+            acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+        }
     }
+    // phase 2: out-of-image taps contribute zero (the clamped loads fetched a valid but irrelevant pixel)
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int hi = h + r - 1;
-        if (hi < 0 || hi >= p.H) continue;
+        const bool row_ok = hi >= 0 && hi < p.H;
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int wi = w + s - 1;
-            if (wi < 0 || wi >= p.W) continue;
-            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(
-                p.x + (((long long)n * p.H + hi) * p.W + wi) * p.x_cstride + p.x_coff + c));
-            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + (r * 3 + s) * p.C + c));
-            acc[0] = fmaf(bf16lo_f(xv.x), bf16lo_f(wv.x), acc[0]);
-            acc[1] = fmaf(bf16hi_f(xv.x), bf16hi_f(wv.x), acc[1]);
-            acc[2] = fmaf(bf16lo_f(xv.y), bf16lo_f(wv.y), acc[2]);
-            acc[3] = fmaf(bf16hi_f(xv.y), bf16hi_f(wv.y), acc[3]);
-            acc[4] = fmaf(bf16lo_f(xv.z), bf16lo_f(wv.z), acc[4]);
-            acc[5] = fmaf(bf16hi_f(xv.z), bf16hi_f(wv.z), acc[5]);
-            acc[6] = fmaf(bf16lo_f(xv.w), bf16lo_f(wv.w), acc[6]);
-            acc[7] = fmaf(bf16hi_f(xv.w), bf16hi_f(wv.w), acc[7]);
+        for (int j = 0; j < P + 2; ++j) {
+            const int wi = w0 + j - 1;
+            const bool ok = row_ok && wi >= 0 && wi < p.W;
+            const uint4 q = xv[r][j];
+            float xf[8];
+            xf[0] = ok ? bf16lo_f(q.x) : 0.f; xf[1] = ok ? bf16hi_f(q.x) : 0.f;
+            xf[2] = ok ? bf16lo_f(q.y) : 0.f; xf[3] = ok ? bf16hi_f(q.y) : 0.f;
+            xf[4] = ok ? bf16lo_f(q.z) : 0.f; xf[5] = ok ? bf16hi_f(q.z) : 0.f;
+            xf[6] = ok ? bf16lo_f(q.w) : 0.f; xf[7] = ok ? bf16hi_f(q.w) : 0.f;
+            // input column j feeds output o = j - s (tap column s), 0 <= o < P
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2) {
+                const int o = j - s2;
+                if (o < 0 || o >= P) continue;
+                const uint4 wq = wv[r * 3 + s2];
+                acc[o][0] = fmaf(xf[0], bf16lo_f(wq.x), acc[o][0]);
+                acc[o][1] = fmaf(xf[1], bf16hi_f(wq.x), acc[o][1]);
+                acc[o][2] = fmaf(xf[2], bf16lo_f(wq.y), acc[o][2]);
+                acc[o][3] = fmaf(xf[3], bf16hi_f(wq.y), acc[o][3]);
+                acc[o][4] = fmaf(xf[4], bf16lo_f(wq.z), acc[o][4]);
+                acc[o][5] = fmaf(xf[5], bf16hi_f(wq.z), acc[o][5]);
+                acc[o][6] = fmaf(xf[6], bf16lo_f(wq.w), acc[o][6]);
+                acc[o][7] = fmaf(xf[7], bf16hi_f(wq.w), acc[o][7]);
+            }
         }
     }
-    if (p.act) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = silu_f(acc[i]);
+    for (int o = 0; o < P; ++o) {
+        const int w = w0 + o;
+        if (w >= p.W) break;
+        const long long pix = row0 + w;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = p.act ? silu_f(acc[o][i]) : acc[o][i];
+        if (p.add) {
+            const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + pix * p.add_cstride + p.add_coff + c));
+            v[0] += bf16lo_f(av.x); v[1] += bf16hi_f(av.x);
+            v[2] += bf16lo_f(av.y); v[3] += bf16hi_f(av.y);
+            v[4] += bf16lo_f(av.z); v[5] += bf16hi_f(av.z);
+            v[6] += bf16lo_f(av.w); v[7] += bf16hi_f(av.w);
+        }
+        uint4 ov;
+        ov.x = pack_bf16x2(v[0], v[1]);
+        ov.y = pack_bf16x2(v[2], v[3]);
+        ov.z = pack_bf16x2(v[4], v[5]);
+        ov.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.y + pix * p.y_cstride + p.y_coff + c) = ov;
     }
-    if (p.add) {
-        const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + pix * p.add_cstride + p.add_coff + c));
-        acc[0] += bf16lo_f(av.x); acc[1] += bf16hi_f(av.x);
-        acc[2] += bf16lo_f(av.y); acc[3] += bf16hi_f(av.y);
-        acc[4] += bf16lo_f(av.z); acc[5] += bf16hi_f(av.z);
-        acc[6] += bf16lo_f(av.w); acc[7] += bf16hi_f(av.w);
-    }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(p.y + pix * p.y_cstride + p.y_coff + c) = o;
 }
 
 // ------------------------------------------------------------------------------------------------ BN fold + pack
@@ -319,8 +366,17 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
     p.W = x->w;
     p.C = x->c;
     p.act = act;
-    const long long total = (long long)x->n * x->h * x->w * (x->c / 8);
-    yl::dwconv3x3_kernel<<<(unsigned)yl::ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    YL_CHECK(x->n <= 65535, YL_ERR_ARG, "batch too large for one launch");
+    const char* e = getenv("YL_DW_STRIP");  // launch-time only (plans are captured into CUDA graphs)
+    const int strip = (e && *e) ? atoi(e) : 2;  // measured: 2-pixel strips are fastest (tools/bench_kernels.py)
+    const int P = strip >= 4 ? 4 : (strip >= 2 ? 2 : 1);
+    const long long per_image = (long long)x->h * yl::ceil_div(x->w, P) * (x->c / 8);
+    YL_CHECK(per_image < (1ll << 31), YL_ERR_ARG, "image too large");
+    const dim3 grid((unsigned)yl::ceil_div64(per_image, 256), (unsigned)x->n, 1), block(256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P == 4) YL_CUDA(yl::launch_kernel(yl::dwconv3x3_kernel<4>, grid, block, 0, s, p));
+    else if (P == 2) YL_CUDA(yl::launch_kernel(yl::dwconv3x3_kernel<2>, grid, block, 0, s, p));
+    else YL_CUDA(yl::launch_kernel(yl::dwconv3x3_kernel<1>, grid, block, 0, s, p));
     YL_LAUNCH_OK("dwconv3x3_kernel");
     return YL_OK;
 }
@@ -332,69 +388,158 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
 // (predictor.py:81-84 `.to(device).float()`), 3x3 stride-2 conv with <= 4 input channels, folded BN, SiLU,
 // writes NHWC bf16.  Replaces a layout pass (read 4.9 MB + write 2.5 MB per image) plus a conv pass with one
 // kernel whose traffic is the algorithmic minimum (read image once, write activations once).
-// One thread = one output pixel x CO channels; weights are staged in shared memory as fp32 [tap][ci][CO] and
-// read as warp-uniform 16-byte broadcasts.
+//
+// The GEMM is M = pixels, N = CO, K = 9*Ci (27 -> padded to 32): too thin for tcgen05 (no TMA im2col of an
+// fp32 NCHW image), but a CUDA-core kernel is FMA/LDS-issue bound at ~4x the HBM time.  So the im2col A
+// fragments are gathered straight into registers (k = tap*Ci + ci, rounded to bf16 exactly like the NHWC
+// ingest would) and multiplied with warp-level mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  A warp walks 64
+// consecutive output pixels of one row in four 16-pixel steps; the weight (B) fragments and biases stay in
+// registers for the whole walk.
 namespace yl {
 
-template <int CO>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int N, int Ci, int H, int W,
-                                                        const __nv_bfloat16* __restrict__ wp, int ci_pad,
-                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
-                                                        long long y_cstride, int y_coff, int Ho, int Wo, int act) {
-    __shared__ __align__(16) float sw[9 * 4 * CO];
-    __shared__ float sb[CO];
-    for (int i = threadIdx.x + threadIdx.y * 32; i < 9 * 4 * CO; i += 256) {
-        const int co = i % CO, ci = (i / CO) % 4, tap = i / (4 * CO);
-        sw[i] = ci < Ci ? __bfloat162float(wp[(long long)co * 9 * ci_pad + tap * ci_pad + ci]) : 0.f;
-    }
-    for (int i = threadIdx.x + threadIdx.y * 32; i < CO; i += 256) sb[i] = bias[i];
-    __syncthreads();
-    const int wo = blockIdx.x * 32 + threadIdx.x;
-    const int ho = blockIdx.y * 8 + threadIdx.y;
-    const int n = blockIdx.z;
-    if (wo >= Wo || ho >= Ho) return;
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
-    float acc[CO];
-#pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = sb[c];
+constexpr int kStemRowPixels = 64;  // output pixels of one row per warp
+constexpr int kStemWarps = 8;       // output rows per block
+
+template <int CO, int KSTEPS>
+__global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
+    const float* __restrict__ x, int N, int Ci, int H, int W, const __nv_bfloat16* __restrict__ wp, int ci_pad,
+    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long y_cstride, int y_coff, int Ho, int Wo,
+    int act) {
+    constexpr int NT = CO / 8;
+    constexpr int NSLOT = KSTEPS * 4;
+    griddep_launch_dependents();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ho = blockIdx.y * kStemWarps + warp;
+    const int n = blockIdx.z;
+    const int wbase = blockIdx.x * kStemRowPixels;
+    if (ho >= Ho) return;
+    const int K = 9 * Ci;
     const long long plane = (long long)H * W;
-    const float* xn = x + (long long)n * Ci * plane;
+
+    // k slots of this thread (fragment layout of mma.m16n8k16: k = 16*ks + {2t, 2t+1, 2t+8, 2t+9})
+    int off[NSLOT];                       // element offset of the slot's tap/channel from (n, 0, 2ho, 2wo)
+    uint32_t m_valid = 0, m_top = 0, m_left = 0, m_bot = 0, m_right = 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int hi = 2 * ho + r - 1;
-        if (hi < 0 || hi >= H) continue;
+    for (int i = 0; i < NSLOT; ++i) {
+        const int k = 16 * (i >> 2) + 2 * t + (i & 1) + ((i >> 1) & 1) * 8;
+        const int tap = k / Ci, ci = k - tap * Ci;
+        const int r = tap / 3, s2 = tap - 3 * r;
+        off[i] = 0;
+        if (k < K) {
+            off[i] = (int)(ci * plane) + (r - 1) * W + (s2 - 1);
+            m_valid |= 1u << i;
+            if (r == 0) m_top |= 1u << i;
+            if (r == 2) m_bot |= 1u << i;
+            if (s2 == 0) m_left |= 1u << i;
+            if (s2 == 2) m_right |= 1u << i;
+        }
+    }
+    // B fragments: b0 = {W[k0][n], W[k0+1][n]}, b1 = {W[k0+8][n], W[k0+9][n]}, k0 = 16*ks + 2t, n = 8*nt + g
+    uint32_t bfrag[KSTEPS][NT][2];
+    float bia[NT][2];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int wi = 2 * wo + s - 1;
-            if (wi < 0 || wi >= W) continue;
-            for (int ci = 0; ci < Ci; ++ci) {
-                // the model consumes bf16 images: round here exactly like the NHWC bf16 ingest did
-                const float xv = __bfloat162float(__float2bfloat16_rn(__ldg(xn + ci * plane + (long long)hi * W + wi)));
-                const float4* wv = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 4 + ci) * CO);
+    for (int nt = 0; nt < NT; ++nt) {
+        const int co = nt * 8 + g;
+        const __nv_bfloat16* wrow = wp + (long long)co * 9 * ci_pad;
 #pragma unroll
-                for (int c4 = 0; c4 < CO / 4; ++c4) {
-                    const float4 w4 = wv[c4];
-                    acc[c4 * 4 + 0] = fmaf(xv, w4.x, acc[c4 * 4 + 0]);
-                    acc[c4 * 4 + 1] = fmaf(xv, w4.y, acc[c4 * 4 + 1]);
-                    acc[c4 * 4 + 2] = fmaf(xv, w4.z, acc[c4 * 4 + 2]);
-                    acc[c4 * 4 + 3] = fmaf(xv, w4.w, acc[c4 * 4 + 3]);
+        for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 16 * ks + 2 * t + e + hh * 8;
+                    uint32_t bits = 0;
+                    if (k < K) {
+                        const int tap = k / Ci, ci = k - tap * Ci;
+                        bits = (uint32_t)__bfloat16_as_ushort(wrow[tap * ci_pad + ci]);
+                    }
+                    v |= bits << (16 * e);
                 }
+                bfrag[ks][nt][hh] = v;
+            }
+        bia[nt][0] = __ldg(bias + nt * 8 + 2 * t);
+        bia[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+    }
+    griddep_wait();
+
+    const float* xrow = x + (long long)n * Ci * plane + (long long)(2 * ho) * W;
+    uint32_t m_row = m_valid;
+    if (ho == 0) m_row &= ~m_top;
+    if (2 * ho + 1 >= H) m_row &= ~m_bot;
+    __nv_bfloat16* yrow = y + ((long long)n * Ho + ho) * Wo * y_cstride + y_coff;
+
+#pragma unroll 1
+    for (int mt = 0; mt < kStemRowPixels / 16; ++mt) {
+        const int wo0 = wbase + mt * 16;
+        if (wo0 >= Wo) break;
+        uint32_t a[KSTEPS][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {      // fragment rows g and g + 8
+            const int wo = wo0 + g + half * 8;
+            uint32_t m = (wo < Wo) ? m_row : 0u;
+            if (wo == 0) m &= ~m_left;
+            if (2 * wo + 1 >= W) m &= ~m_right;
+            const float* px = xrow + 2 * wo;
+            float v[NSLOT];
+#pragma unroll
+            for (int i = 0; i < NSLOT; ++i) v[i] = ((m >> i) & 1u) ? __ldg(px + off[i]) : 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                // a0/a1: k = 2t, 2t+1 (rows g / g+8);  a2/a3: k = 2t+8, 2t+9
+                a[ks][half] = pack_bf16x2(v[ks * 4 + 0], v[ks * 4 + 1]);
+                a[ks][2 + half] = pack_bf16x2(v[ks * 4 + 2], v[ks * 4 + 3]);
+            }
+        }
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            acc[nt][0] = bia[nt][0]; acc[nt][1] = bia[nt][1];
+            acc[nt][2] = bia[nt][0]; acc[nt][3] = bia[nt][1];
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_16816(acc[nt], a[ks], bfrag[ks][nt][0], bfrag[ks][nt][1]);
+        }
+        // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int wo = wo0 + g + half * 8;
+            if (wo >= Wo) continue;
+            __nv_bfloat16* dst = yrow + (long long)wo * y_cstride + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float v0 = acc[nt][half * 2 + 0], v1 = acc[nt][half * 2 + 1];
+                if (act) {
+                    v0 = silu_f(v0);
+                    v1 = silu_f(v1);
+                }
+                *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16x2(v0, v1);
             }
         }
     }
-    __nv_bfloat16* dst = y + (((long long)n * Ho + ho) * Wo + wo) * y_cstride + y_coff;
-#pragma unroll
-    for (int c8 = 0; c8 < CO / 8; ++c8) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = act ? silu_f(acc[c8 * 8 + i]) : acc[c8 * 8 + i];
-        uint4 o;
-        o.x = pack_bf16x2(v[0], v[1]);
-        o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]);
-        o.w = pack_bf16x2(v[6], v[7]);
-        reinterpret_cast<uint4*>(dst)[c8] = o;
-    }
+}
+
+template <int CO>
+static int launch_stem(const float* x, int n, int ci, int h, int w, const __nv_bfloat16* wp, int ci_pad,
+                       const float* bias, __nv_bfloat16* yp, long long cs, int coff, int Ho, int Wo, int act,
+                       cudaStream_t s) {
+    dim3 grid((unsigned)ceil_div(Wo, kStemRowPixels), (unsigned)ceil_div(Ho, kStemWarps), (unsigned)n);
+    dim3 block(32 * kStemWarps, 1, 1);
+    if (9 * ci <= 32)
+        YL_CUDA(launch_kernel(stem_conv_kernel<CO, 2>, grid, block, 0, s, x, n, ci, h, w, wp, ci_pad, bias, yp, cs, coff,
+                              Ho, Wo, act));
+    else
+        YL_CUDA(launch_kernel(stem_conv_kernel<CO, 3>, grid, block, 0, s, x, n, ci, h, w, wp, ci_pad, bias, yp, cs, coff,
+                              Ho, Wo, act));
+    YL_LAUNCH_OK("stem_conv_kernel");
+    return YL_OK;
 }
 
 }  // namespace yl
@@ -406,20 +551,19 @@ extern "C" int yl_stem_conv(const float* x_nchw, int n, int ci, int h, int w, co
     const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
     YL_CHECK(y->dtype == YL_BF16 && y->n == n && y->h == Ho && y->w == Wo, YL_ERR_ARG, "stem output shape mismatch");
     YL_CHECK(y->coff % 8 == 0 && y->cstride % 8 == 0, YL_ERR_ARG, "stem output needs 8-channel alignment");
-    dim3 grid((unsigned)yl::ceil_div(Wo, 32), (unsigned)yl::ceil_div(Ho, 8), (unsigned)n), block(32, 8, 1);
+    YL_CHECK((long long)ci * h * w < (1ll << 31), YL_ERR_ARG, "image too large");
+    YL_CHECK(n <= 65535, YL_ERR_ARG, "batch too large for one launch");
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
     const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w_packed);
     cudaStream_t s = (cudaStream_t)stream;
     switch (y->c) {
-        case 16: yl::stem_conv_kernel<16><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
-        case 32: yl::stem_conv_kernel<32><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
-        case 48: yl::stem_conv_kernel<48><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
-        case 64: yl::stem_conv_kernel<64><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
-        case 96: yl::stem_conv_kernel<96><<<grid, block, 0, s>>>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act); break;
+        case 16: return yl::launch_stem<16>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act, s);
+        case 32: return yl::launch_stem<32>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act, s);
+        case 48: return yl::launch_stem<48>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act, s);
+        case 64: return yl::launch_stem<64>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act, s);
+        case 96: return yl::launch_stem<96>(x_nchw, n, ci, h, w, wp, ci_pad, bias, yp, y->cstride, y->coff, Ho, Wo, act, s);
         default:
             yl::set_error("stem kernel is built for 16/32/48/64/96 output channels (yolo11 n/s/-/m,l/x), got %d", y->c);
             return YL_ERR_UNSUPPORTED;
     }
-    YL_LAUNCH_OK("stem_conv_kernel");
-    return YL_OK;
 }

@@ -51,14 +51,22 @@ struct ConvTcParams {
     int patch, patch_pw, patch_bo;
     CUtensorMap tmW3;            // weights as {ci, co, tap}: box {kblk, co_tile, 9} -> smem [tap][co_tile][kblk]
     uint32_t w_bytes;
+    // resident-weights mode (non-patch, one N tile, small K): all k-iterations' weight tiles are fetched once per
+    // CTA into smem [kiter][co_tile][kblk]; the ring then carries activations only (TMA issue rate, not bytes, is
+    // what bounds the thin layers: ~3.3 clk per box row per SM, tools/tma_bench.cu)
+    int wres;
     uint32_t tmem_cols;
     uint32_t a_bytes, b_bytes;   // per-stage smem footprint (1024-aligned)
+    uint32_t b_region;           // smem bytes of the weight area: ring (stages * b_bytes) or resident block
     uint32_t tx_bytes;           // bytes one stage's two TMA boxes deliver
     // epilogue
-    int cw;                      // columns per chunk (16 or 32)
+    int cw;                      // accumulator columns per TMEM load (16 or 32)
     int nchunks;
-    int stg_row_bytes;           // cw * element size: 32, 64 or 128 (= the staging swizzle span)
-    uint32_t stg_bytes;          // per epilogue group
+    int stg_sub;                 // TMEM chunks per TMA store (1 or 2): a store moves stg_sub * cw channels
+    int nstore;                  // TMA stores per tile = ceil(nchunks / stg_sub)
+    int stg_bufs;                // staging tiles per epilogue group (2 = the store of chunk k overlaps chunk k+1)
+    int stg_row_bytes;           // stg_sub * cw * element size: 32, 64 or 128 (= the staging swizzle span)
+    uint32_t stg_bytes;          // per staging tile
     int y_f32;
     const float* bias;
     int n_bias;                  // valid bias entries (co_pad)
@@ -83,6 +91,10 @@ __device__ __forceinline__ void tmem_ld_cw<32>(uint32_t taddr, uint32_t (&r)[32]
 }
 
 // One epilogue group (4 warps, thread = accumulator row) draining the tiles of its accumulator stage.
+// A "store chunk" is stg_sub TMEM chunks (<= 128 B per pixel row) staged in one swizzled tile and written by
+// one TMA store.  With two staging tiles the store of chunk k is issued after the barrier of chunk k+1, so the
+// group never waits for a TMA store to drain its source: one named barrier per store chunk, and the smem read
+// of store k overlaps the TMEM load + math of chunk k+1.
 template <int CW>
 __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, int q, int lane, int gtid,
                                                  uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -94,6 +106,13 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
     const uint32_t swz_mask = (uint32_t)(p.stg_row_bytes / 16 - 1);  // 1, 3 or 7 sixteen-byte chunks
     const uint32_t row_off = (uint32_t)row * (uint32_t)p.stg_row_bytes;
     const uint32_t stg_base = smem_u32(stg);
+    const uint32_t sub_bytes = (uint32_t)CW * (p.y_f32 ? 4u : 2u);
+    const bool dbl = p.stg_bufs == 2;
+    // the first warp of the group owns the TMA stores; one elected lane issues / commits / waits on them
+    const bool leader = (gtid < 32) && elect_one();
+    uint32_t kstore = 0;                       // running store-chunk counter (selects the staging tile)
+    int pend = 0, pc0 = 0, pw0 = 0, ph0 = 0, pi0 = 0;  // filled tile whose TMA store is not issued yet
+    uint32_t pbuf = 0;
 
     int lt = g;
     for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, lt += 2) {
@@ -117,78 +136,117 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.acc_stride);
 
-        for (int c = 0; c < p.nchunks; ++c) {
-            const int col0 = n0 + c * CW;  // first output channel of this chunk
-            uint32_t acc[CW];
-            tmem_ld_cw<CW>(taddr + (uint32_t)(c * CW), acc);
-            // residual rows are independent of the accumulator: issue the loads under the TMEM latency
-            uint4 rv[CW / 8];
-#pragma unroll
-            for (int i = 0; i < CW / 8; ++i) {
-                rv[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (resrow && col0 + i * 8 < p.res_c) rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
-            }
-            tmem_ld_wait();
-            if (c == p.nchunks - 1) {
-                // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[g]);
-            }
-            float v[CW];
-#pragma unroll
-            for (int i = 0; i < CW; i += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + i);
-                v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
-                v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
-                v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
-                v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
-            }
-            if (p.act) {
-#pragma unroll
-                for (int i = 0; i < CW; ++i) v[i] = silu_fast(v[i]);
-            }
-            if (p.res) {
+        for (int s = 0; s < p.nstore; ++s, ++kstore) {
+            const uint32_t buf = dbl ? (kstore & 1u) * p.stg_bytes : 0u;
+            for (int u = 0; u < p.stg_sub; ++u) {
+                const int c = s * p.stg_sub + u;
+                if (c >= p.nchunks) break;
+                const int col0 = n0 + c * CW;  // first output channel of this chunk
+                uint32_t acc[CW];
+                tmem_ld_cw<CW>(taddr + (uint32_t)(c * CW), acc);
+                // residual rows are independent of the accumulator: issue the loads under the TMEM latency
+                uint4 rv[CW / 8];
 #pragma unroll
                 for (int i = 0; i < CW / 8; ++i) {
-                    v[i * 8 + 0] += bf16lo_f(rv[i].x); v[i * 8 + 1] += bf16hi_f(rv[i].x);
-                    v[i * 8 + 2] += bf16lo_f(rv[i].y); v[i * 8 + 3] += bf16hi_f(rv[i].y);
-                    v[i * 8 + 4] += bf16lo_f(rv[i].z); v[i * 8 + 5] += bf16hi_f(rv[i].z);
-                    v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
+                    rv[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (resrow && col0 + i * 8 < p.res_c)
+                        rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
                 }
-            }
-            // the previous TMA store of this group must have finished reading the staging tile
-            if (gtid == 0) bulk_wait_read<0>();
-            named_bar_sync(1 + g, kEpiGroupThreads);
-            if (p.y_f32) {
-#pragma unroll
-                for (int j = 0; j < CW / 4; ++j) {
-                    uint32_t off = row_off + (uint32_t)j * 16u;
-                    off ^= ((off >> 7) & swz_mask) << 4;
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + off), "f"(v[4 * j]),
-                                 "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                                 : "memory");
+                tmem_ld_wait();
+                if (c == p.nchunks - 1) {
+                    // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[g]);
                 }
-            } else {
+                float v[CW];
 #pragma unroll
-                for (int j = 0; j < CW / 8; ++j) {
-                    uint32_t off = row_off + (uint32_t)j * 16u;
-                    off ^= ((off >> 7) & swz_mask) << 4;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + off),
-                                 "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
-                                 "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
-                                 : "memory");
+                for (int i = 0; i < CW; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + i);
+                    v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
+                    v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+                    v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
+                    v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+                }
+                if (p.act) {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = silu_fast(v[i]);
+                }
+                if (p.res) {
+#pragma unroll
+                    for (int i = 0; i < CW / 8; ++i) {
+                        v[i * 8 + 0] += bf16lo_f(rv[i].x); v[i * 8 + 1] += bf16hi_f(rv[i].x);
+                        v[i * 8 + 2] += bf16lo_f(rv[i].y); v[i * 8 + 3] += bf16hi_f(rv[i].y);
+                        v[i * 8 + 4] += bf16lo_f(rv[i].z); v[i * 8 + 5] += bf16hi_f(rv[i].z);
+                        v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
+                    }
+                }
+                if (u == 0) {
+                    // the staging tile about to be overwritten must have been drained by its last TMA store:
+                    // every committed store has (two tiles: the newest committed one used this tile, the one
+                    // filled last is still pending; one tile: the newest committed one used it)
+                    if (leader) bulk_wait_read<0>();
+                    named_bar_sync(1 + g, kEpiGroupThreads);
+                    // ... and the barrier also says every thread has written + fenced the pending tile
+                    if (pend) {
+                        if (leader) {
+                            for (int m = p.y_map_first; m < p.y_map_last; ++m)
+                                tma_store_4d(&p.tmY[m], stg + pbuf, pc0, pw0, ph0, pi0);
+                            bulk_commit();
+                        }
+                        pend = 0;
+                    }
+                }
+                const uint32_t base_off = row_off + (uint32_t)u * sub_bytes;
+                if (p.y_f32) {
+#pragma unroll
+                    for (int j = 0; j < CW / 4; ++j) {
+                        uint32_t off = base_off + (uint32_t)j * 16u;
+                        off ^= ((off >> 7) & swz_mask) << 4;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + buf + off),
+                                     "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                     : "memory");
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CW / 8; ++j) {
+                        uint32_t off = base_off + (uint32_t)j * 16u;
+                        off ^= ((off >> 7) & swz_mask) << 4;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + buf + off),
+                                     "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                                     "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                                     "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                                     "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                                     : "memory");
+                    }
                 }
             }
             fence_proxy_async_smem();
-            named_bar_sync(1 + g, kEpiGroupThreads);
-            if (gtid == 0) {
-                for (int m = p.y_map_first; m < p.y_map_last; ++m) tma_store_4d(&p.tmY[m], stg, col0, w0, h0, i0);
-                bulk_commit();
+            if (dbl) {
+                pend = 1;
+                pbuf = buf;
+                pc0 = n0 + s * p.stg_sub * CW;
+                pw0 = w0;
+                ph0 = h0;
+                pi0 = i0;
+            } else {
+                named_bar_sync(1 + g, kEpiGroupThreads);
+                if (leader) {
+                    for (int m = p.y_map_first; m < p.y_map_last; ++m)
+                        tma_store_4d(&p.tmY[m], stg, n0 + s * p.stg_sub * CW, w0, h0, i0);
+                    bulk_commit();
+                }
             }
         }
     }
-    if (gtid == 0) bulk_wait<0>();
+    if (dbl) {
+        named_bar_sync(1 + g, kEpiGroupThreads);
+        if (leader && pend) {
+            for (int m = p.y_map_first; m < p.y_map_last; ++m) tma_store_4d(&p.tmY[m], stg + pbuf, pc0, pw0, ph0, pi0);
+            bulk_commit();
+        }
+    }
+    if (leader) bulk_wait<0>();
 }
 
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
@@ -196,7 +254,9 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
 // overlaps the loads and MMAs of tiles i+1, i+2.
 __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0 so the compiler treats the warp index (and every role / tile index derived from it)
+    // as warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     // ---- shared memory carve-up (1024-B aligned: required by the 128-B swizzle atom)
@@ -204,8 +264,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* sA = base;
     uint8_t* sB = sA + (size_t)p.stages * p.a_bytes;
-    uint8_t* sStg = sB + (p.patch ? (size_t)p.b_bytes : (size_t)p.stages * p.b_bytes);  // [2 groups][stg_bytes]
-    float* sbias = reinterpret_cast<float*>(sStg + 2 * (size_t)p.stg_bytes);
+    uint8_t* sStg = sB + (size_t)p.b_region;  // [2 groups][stg_bufs][stg_bytes]
+    float* sbias = reinterpret_cast<float*>(sStg + 2 * (size_t)p.stg_bufs * p.stg_bytes);
     const int nbias = p.n_tiles * p.co_tile + 32;                          // chunk tails read past co_tile
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + ((nbias + 3) & ~3));
     uint64_t* empty_bar = full_bar + p.stages;
@@ -214,6 +274,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     uint64_t* w_bar = tempty_bar + 2;             // patch mode: resident weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
+    // programmatic dependent launch: let the next kernel of the stream start its prologue as our CTAs retire
+    griddep_launch_dependents();
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -240,30 +302,51 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched only constants (weights' bias, tensor maps); activations written by the
+    // previous kernel of the stream are read / overwritten only after it has completed
+    griddep_wait();
 
     const int taps = p.ksize * p.ksize;
     const int kiters = taps * p.cin_blocks;
 
+    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
+    // same coordinates / descriptors, so they live in uniform registers) and one elected lane issues the TMA /
+    // tcgen05 instructions: a `lane == 0` branch instead makes every operand "possibly divergent" and costs a
+    // register->uniform waterfall loop per issued instruction.
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && p.patch) {
-            mbar_expect_tx(w_bar, p.w_bytes);
-            tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const bool leader = elect_one();
+        int st = 0;
+        uint32_t ph = 0;  // ring position / phase of the stage being filled
+        if (p.patch) {
+            if (leader) {
+                mbar_expect_tx(w_bar, p.w_bytes);
+                tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
+            }
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int mt = tile;
                 const int w0 = (mt % p.tiles_w) * p.TW;
                 mt /= p.tiles_w;
                 const int h0 = (mt % p.tiles_h) * p.TH;
                 const int i0 = mt / p.tiles_h;
-                const int st = it % p.stages;
-                const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(&empty_bar[st], ph_bit ^ 1u);
-                mbar_expect_tx(&full_bar[st], p.tx_bytes);
-                tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[0], &full_bar[st], 0, w0 - 1, h0 - 1, i0);
+                mbar_wait(&empty_bar[st], ph ^ 1u);
+                if (leader) {
+                    mbar_expect_tx(&full_bar[st], p.tx_bytes);
+                    tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[0], &full_bar[st], 0, w0 - 1, h0 - 1, i0);
+                }
+                if (++st == p.stages) {
+                    st = 0;
+                    ph ^= 1u;
+                }
             }
-        } else if (lane == 0) {
-            int it = 0;
+        } else {
+            if (p.wres && leader) {
+                mbar_expect_tx(w_bar, p.w_bytes);
+                int ki = 0;
+                for (int tap = 0; tap < taps; ++tap)
+                    for (int cb = 0; cb < p.cin_blocks; ++cb, ++ki)
+                        tma_load_2d(sB + (size_t)ki * p.b_bytes, &p.tmB, w_bar, tap * p.ci_pad + cb * p.kblk, 0);
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 int mt = tile / p.n_tiles;
@@ -272,90 +355,112 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
                 const int h0 = (mt % p.tiles_h) * p.TH;
                 const int i0 = (mt / p.tiles_h) * p.TN;
                 const int n0 = nt * p.co_tile;
-                for (int tap = 0; tap < taps; ++tap) {
-                    const int r = tap / p.ksize, s = tap - r * p.ksize;
-                    const int offh = r - p.pad, offw = s - p.pad;
-                    int map = 0, dh = offh, dw = offw;
-                    if (p.stride == 2) {
-                        const int ph = offh & 1, pw = offw & 1;
-                        map = ph * 2 + pw;
-                        dh = (offh - ph) >> 1;
-                        dw = (offw - pw) >> 1;
-                    }
-                    for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
-                        const int st = it % p.stages;
-                        const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
-                        mbar_wait(&empty_bar[st], ph_bit ^ 1u);
-                        mbar_expect_tx(&full_bar[st], p.tx_bytes);
-                        tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[map], &full_bar[st], cb * p.kblk, w0 + dw,
-                                    h0 + dh, i0);
-                        tma_load_2d(sB + (size_t)st * p.b_bytes, &p.tmB, &full_bar[st],
-                                    tap * p.ci_pad + cb * p.kblk, n0);
+                int tap = 0;
+                for (int r = 0; r < p.ksize; ++r) {
+                    for (int s2 = 0; s2 < p.ksize; ++s2, ++tap) {
+                        const int offh = r - p.pad, offw = s2 - p.pad;
+                        int map = 0, dh = offh, dw = offw;
+                        if (p.stride == 2) {
+                            const int ph2 = offh & 1, pw2 = offw & 1;
+                            map = ph2 * 2 + pw2;
+                            dh = (offh - ph2) >> 1;
+                            dw = (offw - pw2) >> 1;
+                        }
+                        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                            mbar_wait(&empty_bar[st], ph ^ 1u);
+                            if (leader) {
+                                mbar_expect_tx(&full_bar[st], p.tx_bytes);
+                                tma_load_4d(sA + (size_t)st * p.a_bytes, &p.tmA[map], &full_bar[st], cb * p.kblk,
+                                            w0 + dw, h0 + dh, i0);
+                                if (!p.wres)
+                                    tma_load_2d(sB + (size_t)st * p.b_bytes, &p.tmB, &full_bar[st],
+                                                tap * p.ci_pad + cb * p.kblk, n0);
+                            }
+                            if (++st == p.stages) {
+                                st = 0;
+                                ph ^= 1u;
+                            }
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && p.patch) {
-            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.co_tile);
-            const uint32_t rb = (uint32_t)p.kblk * 2u;
-            const int ksteps = p.kblk / 16;
-            const uint32_t sbo = (uint32_t)p.patch_pw * rb;       // next 8-row group = next patch row (TW == 8)
-            const uint32_t wtap = (uint32_t)p.co_tile * rb;       // bytes of one tap's weight tile
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.co_tile);
+        const uint32_t rb = (uint32_t)p.kblk * 2u;  // operand row bytes = swizzle span
+        const int ksteps = p.kblk / 16;
+        int st = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        if (p.patch || p.wres) {
             mbar_wait(w_bar, 0);
             tc_fence_after();
-            int lt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-                const int acc = lt & 1;
-                const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+        }
+        if (p.patch) {
+            const uint32_t sbo = (uint32_t)p.patch_pw * rb;       // next 8-row group = next patch row (TW == 8)
+            const uint32_t wtap = (uint32_t)p.co_tile * rb;       // bytes of one tap's weight tile
+            const uint32_t b0 = smem_u32(sB);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+                mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-                const int st = lt % p.stages;
-                mbar_wait(&full_bar[st], (uint32_t)(lt / p.stages) & 1u);
-                tc_fence_after();
                 const uint32_t a0 = smem_u32(sA + (size_t)st * p.a_bytes);
-                const uint32_t b0 = smem_u32(sB);
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int r = tap / 3, s = tap - 3 * r;
-                    const uint32_t astart = a0 + (uint32_t)(r * p.patch_pw + s) * rb;
-                    const uint32_t bo = p.patch_bo ? ((astart >> 7) & 7u) : 0u;
-                    const uint64_t da = umma_desc_kmajor_ex(astart, rb, sbo, bo);
-                    const uint64_t db = umma_desc_kmajor(b0 + (uint32_t)tap * wtap, rb);
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                  (tap > 0 || k > 0) ? 1u : 0u);
+                if (leader) {
+                    uint32_t first = 0;
+                    uint32_t arow = a0;
+                    uint32_t bt = b0;
+                    for (int r = 0; r < 3; ++r, arow += (uint32_t)p.patch_pw * rb) {
+                        for (int s2 = 0; s2 < 3; ++s2, bt += wtap) {
+                            const uint32_t astart = arow + (uint32_t)s2 * rb;
+                            const uint32_t bo = p.patch_bo ? ((astart >> 7) & 7u) : 0u;
+                            const uint64_t da = umma_desc_kmajor_ex(astart, rb, sbo, bo);
+                            const uint64_t db = umma_desc_kmajor(bt, rb);
+                            for (int k = 0; k < ksteps; ++k) {
+                                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+                                first = 1u;
+                            }
+                        }
+                    }
+                    umma_commit(&empty_bar[st]);
+                    umma_commit(&tfull_bar[acc]);
                 }
-                umma_commit(&empty_bar[st]);
-                umma_commit(&tfull_bar[acc]);
+                if (++st == p.stages) {
+                    st = 0;
+                    ph ^= 1u;
+                }
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1u;
             }
-        } else if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.co_tile);
-            const uint32_t row_bytes = (uint32_t)p.kblk * 2u;
-            const int ksteps = p.kblk / 16;
-            int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-                const int acc = lt & 1;
-                const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+        } else {
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int st = it % p.stages;
-                    const uint32_t ph_bit = (uint32_t)(it / p.stages) & 1u;
-                    mbar_wait(&full_bar[st], ph_bit);
+                for (int ki = 0; ki < kiters; ++ki) {
+                    mbar_wait(&full_bar[st], ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_kmajor(smem_u32(sA + (size_t)st * p.a_bytes), row_bytes);
-                    const uint64_t db = umma_desc_kmajor(smem_u32(sB + (size_t)st * p.b_bytes), row_bytes);
-                    for (int k = 0; k < ksteps; ++k) {
-                        // advance 16 bf16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                  (ki > 0 || k > 0) ? 1u : 0u);
+                    if (leader) {
+                        const uint64_t da = umma_desc_kmajor(smem_u32(sA + (size_t)st * p.a_bytes), rb);
+                        const uint64_t db = umma_desc_kmajor(smem_u32(sB + (size_t)(p.wres ? ki : st) * p.b_bytes), rb);
+                        for (int k = 0; k < ksteps; ++k) {
+                            // advance 16 bf16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                      (ki > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[st]);
                     }
-                    umma_commit(&empty_bar[st]);
+                    if (++st == p.stages) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (leader) umma_commit(&tfull_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1u;
             }
         }
     } else {
@@ -364,7 +469,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         const int g = e >> 2;    // epilogue group = accumulator stage
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         const int gtid = (e & 3) * 32 + lane;
-        uint8_t* stg = sStg + (size_t)g * p.stg_bytes;
+        uint8_t* stg = sStg + (size_t)g * p.stg_bufs * p.stg_bytes;
         if (p.cw == 32)
             conv_tc_epilogue<32>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
         else
@@ -525,7 +630,9 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     p.stride = a->stride;
     p.pad = pad;
     p.ci_pad = a->ci_pad;
-    p.kblk = x.c >= 64 ? 64 : (x.c >= 32 ? 32 : 16);
+    // channel block = TMA box row: one 128-B row costs the TMA unit about as much as a 32-B row, so round the
+    // channel count up (48 -> one 64-wide block whose tail is OOB zero fill) rather than splitting it
+    p.kblk = x.c > 32 ? 64 : (x.c > 16 ? 32 : 16);
     p.cin_blocks = ceil_div(x.c, p.kblk);
     const CUtensorMapSwizzle sw = swizzle_for_bytes(p.kblk * 2);
     const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -541,7 +648,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     if (a->k == 3 && a->stride == 1 && x.c <= 64 && n_tiles == 1 && env_int("YL_PATCH", 1)) {
         const int kb = env_int("YL_PATCH_K64", 0) ? 64 : p.kblk;
         const double eff = (double)Ho * Wo / ((double)ceil_div(Wo, 8) * 8 * ceil_div(Ho, 16) * 16);
-        if (9 * p.co_tile * kb * 2 <= 40 * 1024 && eff >= 0.6) {
+        if (9 * p.co_tile * kb * 2 <= env_int("YL_PATCH_WMAX_KB", 80) * 1024 && eff >= 0.6) {
             patch = true;
             p.kblk = kb;
             p.cin_blocks = 1;
@@ -629,33 +736,12 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
         if (!encode_map(&p.tmB, bf, const_cast<void*>(a->w), 2, dims, str, box, sw)) return YL_ERR_CUDA;
     }
 
-    // epilogue: chunk width, staging tile and destination tensor maps
+    // epilogue chunking
     p.y_f32 = (y.dtype == YL_F32);
     const int oes = p.y_f32 ? 4 : 2;
     p.cw = p.co_tile >= 32 ? 32 : 16;
     p.nchunks = ceil_div(p.co_tile, p.cw);
     p.acc_stride = p.nchunks * p.cw;
-    p.stg_row_bytes = p.cw * oes;
-    p.stg_bytes = 128u * (uint32_t)p.stg_row_bytes;  // multiple of 1024 for every (cw, dtype) except 16 x bf16
-    if (p.stg_bytes < 1024u) p.stg_bytes = 1024u;
-    p.stg_bytes = (p.stg_bytes + 1023u) & ~1023u;
-    {
-        const CUtensorMapSwizzle osw = swizzle_for_bytes(p.stg_row_bytes);
-        uint32_t obox[4] = {(uint32_t)p.cw, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-        if (a->upsample2x) {
-            if (!encode_out_maps(&p.tmY[1], y, Ho, Wo, x.n, false, true, obox, osw)) return YL_ERR_CUDA;
-            p.y_map_first = 1;
-            p.y_map_last = 5;
-        } else {
-            if (!encode_out_maps(&p.tmY[0], y, Ho, Wo, x.n, flat, false, obox, osw)) return YL_ERR_CUDA;
-            p.y_map_first = 0;
-            p.y_map_last = 1;
-            if (a->y_up.data) {
-                if (!encode_out_maps(&p.tmY[1], a->y_up, Ho, Wo, x.n, false, true, obox, osw)) return YL_ERR_CUDA;
-                p.y_map_last = 5;
-            }
-        }
-    }
 
     p.a_bytes = 128u * p.kblk * 2u;
     p.b_bytes = ((uint32_t)p.co_tile * p.kblk * 2u + 1023u) & ~1023u;
@@ -674,19 +760,68 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     while ((int)cols < 2 * p.acc_stride) cols <<= 1;
     YL_CHECK(cols <= 512, YL_ERR_UNSUPPORTED, "accumulator needs %u TMEM columns", cols);
     p.tmem_cols = cols;
-    const int ctas_per_sm = (cols <= 256) ? 2 : 1;
+    int ctas_per_sm = (cols <= 256) ? 2 : 1;
+    if (patch && p.b_bytes > 40u * 1024u) ctas_per_sm = 1;  // big resident 9-tap weights: one CTA owns the SM
+    const int kiters_total = a->k * a->k * p.cin_blocks;
+    const size_t wres_bytes = (size_t)kiters_total * p.b_bytes;
+    if (!patch && n_tiles == 1 && env_int("YL_WRES", 1) &&
+        wres_bytes <= (size_t)(ctas_per_sm == 2 ? 48 : 120) * 1024) {
+        p.wres = 1;
+        p.w_bytes = (uint32_t)kiters_total * (uint32_t)p.co_tile * p.kblk * 2u;
+        p.tx_bytes = (uint32_t)(p.TW * p.TH * p.TN) * p.kblk * 2u;
+    }
     const int nbias = n_tiles * p.co_tile + 32;
-    const size_t fixed = 1024 + 2 * (size_t)p.stg_bytes + (size_t)((nbias + 3) & ~3) * 4 + 16;
-    const uint32_t stage_bytes = patch ? p.a_bytes : p.a_bytes + p.b_bytes;
-    const size_t fixed_b = patch ? p.b_bytes : 0;
-    const size_t budget = (size_t)(ctas_per_sm == 2 ? 112 * 1024 : 224 * 1024) - fixed - fixed_b - 16 * 24 - 64;
-    int stages = (int)(budget / stage_bytes);
+    const uint32_t stage_bytes = (patch || p.wres) ? p.a_bytes : p.a_bytes + p.b_bytes;
+    const size_t fixed_b = patch ? p.b_bytes : (p.wres ? wres_bytes : 0);
+    const size_t cta_smem = (size_t)(ctas_per_sm == 2 ? 112 * 1024 : 224 * 1024);
+
+    // staging: prefer 128-B pixel rows per TMA store (two TMEM chunks of bf16) and two staging tiles per
+    // epilogue group (the store of chunk k overlaps chunk k+1); fall back when the operand ring would get
+    // too shallow to cover the HBM latency
+    int sub_pref = (!p.y_f32 && p.cw == 32 && p.nchunks >= 2) ? 2 : 1;
+    if (n_tiles > 1 && (p.nchunks & 1)) sub_pref = 1;  // a half-filled store row would spill into the next N tile
+    sub_pref = env_int("YL_STG_SUB", sub_pref) >= 2 ? sub_pref : 1;
+    const int bufs_pref = env_int("YL_STG_BUFS", 2) >= 2 ? 2 : 1;
+    const int cand[4][2] = {{sub_pref, bufs_pref}, {1, bufs_pref}, {sub_pref, 1}, {1, 1}};
+    size_t fixed = 0;
+    int stages = 0;
+    for (int ci = 0; ci < 4; ++ci) {
+        p.stg_sub = cand[ci][0];
+        p.stg_bufs = cand[ci][1];
+        p.stg_row_bytes = p.stg_sub * p.cw * oes;
+        p.stg_bytes = (128u * (uint32_t)p.stg_row_bytes + 1023u) & ~1023u;  // 128 rows; 1024-B swizzle atoms
+        fixed = 1024 + 2 * (size_t)p.stg_bufs * p.stg_bytes + (size_t)((nbias + 3) & ~3) * 4 + 16;
+        const long long budget = (long long)cta_smem - (long long)fixed - (long long)fixed_b - 16 * 24 - 64;
+        stages = budget > 0 ? (int)(budget / stage_bytes) : 0;
+        if (stages >= 3 || (stages >= 2 && (size_t)stages * stage_bytes >= 40 * 1024)) break;
+    }
+    p.nstore = ceil_div(p.nchunks, p.stg_sub);
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;
+    p.b_region = (uint32_t)((patch || p.wres) ? fixed_b : (size_t)stages * p.b_bytes);
     const size_t smem = fixed + fixed_b + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 16;
     YL_CHECK((int)smem <= g_max_dyn_smem, YL_ERR_UNSUPPORTED, "conv tile needs %zu B smem (max %d)", smem,
              g_max_dyn_smem);
+
+    // destination tensor maps: box = one store chunk of one tile
+    {
+        const CUtensorMapSwizzle osw = swizzle_for_bytes(p.stg_row_bytes);
+        uint32_t obox[4] = {(uint32_t)(p.stg_sub * p.cw), (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        if (a->upsample2x) {
+            if (!encode_out_maps(&p.tmY[1], y, Ho, Wo, x.n, false, true, obox, osw)) return YL_ERR_CUDA;
+            p.y_map_first = 1;
+            p.y_map_last = 5;
+        } else {
+            if (!encode_out_maps(&p.tmY[0], y, Ho, Wo, x.n, flat, false, obox, osw)) return YL_ERR_CUDA;
+            p.y_map_first = 0;
+            p.y_map_last = 1;
+            if (a->y_up.data) {
+                if (!encode_out_maps(&p.tmY[1], a->y_up, Ho, Wo, x.n, false, true, obox, osw)) return YL_ERR_CUDA;
+                p.y_map_last = 5;
+            }
+        }
+    }
 
     p.bias = a->bias;
     p.n_bias = a->co_pad;
@@ -698,7 +833,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
 
     int grid = g_num_sms * ctas_per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv_tc_kernel<<<grid, kConvTcThreads, smem, stream>>>(p);
+    YL_CUDA(launch_kernel(conv_tc_kernel, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
     YL_LAUNCH_OK("conv_tc_kernel");
     return YL_OK;
 }

@@ -24,6 +24,8 @@ struct DecodeParams {
 __global__ void __launch_bounds__(256) detect_decode_kernel(const DecodeParams p) {
     extern __shared__ float tile[];  // [32][no + 1]
     __shared__ float dist[4][32];
+    griddep_launch_dependents();
+    griddep_wait();
     const int b = blockIdx.y;
     int lvl = 0;
     while (lvl + 1 < p.nl && (int)blockIdx.x >= p.tile0[lvl + 1]) ++lvl;
@@ -154,7 +156,7 @@ extern "C" int yl_detect_decode(const yl_tensor* levels, int nl, const float* st
     const size_t smem = (size_t)32 * (no + 1) * sizeof(float);
     YL_CHECK(smem <= 48 * 1024, YL_ERR_UNSUPPORTED, "too many head channels (%d)", no);
     dim3 grid((unsigned)tiles, (unsigned)levels[0].n, 1);
-    yl::detect_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    YL_CUDA(yl::launch_kernel(yl::detect_decode_kernel, grid, dim3(256), smem, (cudaStream_t)stream, p));
     YL_LAUNCH_OK("detect_decode_kernel");
     return YL_OK;
 }

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__
 __global__ void __launch_bounds__(256) copy_slice_kernel(const __nv_bfloat16* __restrict__ x, long long x_cstride,
                                                          int x_coff, __nv_bfloat16* __restrict__ y,
                                                          long long y_cstride, int y_coff, int C, long long pixels) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int groups = C >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= pixels * groups) return;
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
                                                          int x_coff, __nv_bfloat16* __restrict__ y,
                                                          long long y_cstride, int y_coff, int C, int N, int H, int W) {
     // thread = (output pixel, 8-channel group): reads are re-used 4x through L1/L2, writes are coalesced
+    griddep_launch_dependents();
+    griddep_wait();
     const int groups = C >> 3;
     const int Ho = 2 * H, Wo = 2 * W;
     const long long total = (long long)N * Ho * Wo * groups;
@@ -122,9 +126,10 @@ int yl_copy_slice(const yl_tensor* x, const yl_tensor* y, void* stream) {
     YL_CHECK(yl::aligned8(x) && yl::aligned8(y), YL_ERR_ARG, "copy_slice needs 8-channel alignment");
     const long long pixels = (long long)x->n * x->h * x->w;
     const long long total = pixels * (x->c / 8);
-    yl::copy_slice_kernel<<<(unsigned)yl::ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x->data), x->cstride, x->coff, reinterpret_cast<__nv_bfloat16*>(y->data),
-        y->cstride, y->coff, x->c, pixels);
+    YL_CUDA(yl::launch_kernel(yl::copy_slice_kernel, dim3((unsigned)yl::ceil_div64(total, 256)), dim3(256), 0,
+                              (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(x->data),
+                              (long long)x->cstride, x->coff, reinterpret_cast<__nv_bfloat16*>(y->data),
+                              (long long)y->cstride, y->coff, x->c, pixels));
     YL_LAUNCH_OK("copy_slice_kernel");
     return YL_OK;
 }
@@ -136,9 +141,10 @@ int yl_upsample2x(const yl_tensor* x, const yl_tensor* y, void* stream) {
              "upsample2x shape mismatch");
     YL_CHECK(yl::aligned8(x) && yl::aligned8(y), YL_ERR_ARG, "upsample2x needs 8-channel alignment");
     const long long total = (long long)y->n * y->h * y->w * (y->c / 8);
-    yl::upsample2x_kernel<<<(unsigned)yl::ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x->data), x->cstride, x->coff, reinterpret_cast<__nv_bfloat16*>(y->data),
-        y->cstride, y->coff, x->c, x->n, x->h, x->w);
+    YL_CUDA(yl::launch_kernel(yl::upsample2x_kernel, dim3((unsigned)yl::ceil_div64(total, 256)), dim3(256), 0,
+                              (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(x->data),
+                              (long long)x->cstride, x->coff, reinterpret_cast<__nv_bfloat16*>(y->data),
+                              (long long)y->cstride, y->coff, x->c, x->n, x->h, x->w));
     YL_LAUNCH_OK("upsample2x_kernel");
     return YL_OK;
 }

@@ -167,6 +167,10 @@ __device__ __forceinline__ bool iou_suppresses(const float4 bi, float ai, const 
     const float w = (0.f < dw) ? dw : 0.f;  // std::max(0, xx2 - xx1)
     const float h = (0.f < dh) ? dh : 0.f;
     const float inter = __fmul_rn(w, h);
+    // disjoint boxes (the common case once classes are offset apart): inter == +0, so ovr is 0 or NaN (0/0) and
+    // `ovr > thr` is false for every thr >= 0 -- skip the IEEE division.  A NaN inter fails this test and takes
+    // the division like the reference does.
+    if (inter == 0.f) return false;
     const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
     return ovr > thr;
 }
@@ -226,7 +230,7 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long* skeys, in
 // max_det = 300 the greedy scan almost always finishes inside the first round.
 constexpr int kBins = 4096;
 constexpr int kRoundTarget = 1024;
-constexpr int kBinMax = 4096;                     // a single bin larger than this falls back to radix select
+constexpr int kBinRoundMax = 4096;                // a bin round larger than this switches the image to radix rounds
 constexpr int kDirectSort = 2048;                 // at most this many candidates: sort them all directly
 __device__ __forceinline__ int key_bin(unsigned long long k) {
     const float t = desc_to_score((uint32_t)(k >> 32)) * (float)kBins;
@@ -275,11 +279,10 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
         __syncthreads();
         // block-wide inclusive scan, kBins / kSelThreads (= 4) bins per thread
         constexpr int PER = kBins / kSelThreads;
-        uint32_t v[PER], tsum = 0, big = 0;
+        uint32_t v[PER], tsum = 0;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             v[i] = cum[tid * PER + i];
-            big |= (v[i] > (uint32_t)kBinMax);
             tsum += v[i];
         }
         uint32_t incl = tsum;
@@ -288,7 +291,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             if (lane >= o) incl += t;
         }
         if (lane == 31) hist[warp] = incl;
-        use_bins = !__syncthreads_or((int)big);
+        use_bins = true;
+        __syncthreads();
         if (warp == 0) {
             const uint32_t w = hist[lane];
             uint32_t wi = w;
@@ -320,92 +324,124 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             for (int i = n + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
             __syncthreads();
             block_bitonic_sort(skeys, P, tid);
-        } else if (use_bins) {
-            // the best ~kRoundTarget unconsumed candidates: bins [bpos, e)
-            if (tid == 0) {
-                const uint32_t base = bpos ? cum[bpos - 1] : 0u;
-                int lo_b = bpos, hi_b = kBins - 1;  // smallest e-1 with cum[e-1] - base >= target (or last bin)
-                while (lo_b < hi_b) {
-                    const int mid = (lo_b + hi_b) >> 1;
-                    if (cum[mid] - base >= (uint32_t)kRoundTarget) hi_b = mid; else lo_b = mid + 1;
-                }
-                misc[0] = lo_b + 1;
-                misc[1] = (int)(cum[lo_b] - base);
-                misc[2] = 0;
-            }
-            __syncthreads();
-            const int e = misc[0];
-            const int mr = misc[1];  // <= kRoundTarget - 1 + kBinMax keys fall into this round
-            for (int i0 = 0; i0 < n; i0 += kSelThreads) {
-                const int i = i0 + tid;
-                unsigned long long k = 0;
-                bool take = false;
-                if (i < n) {
-                    k = gkeys[i];
-                    const int kb = key_bin(k);
-                    take = kb >= bpos && kb < e;
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, take);
-                if (bal) {
-                    int pos0 = 0;
-                    if (lane == 0) pos0 = atomicAdd(&misc[2], __popc(bal));
-                    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                    if (take) skeys[pos0 + __popc(bal & ((1u << lane) - 1u))] = k;
-                }
-            }
-            __syncthreads();
-            int P = 32;
-            while (P < mr) P <<= 1;
-            for (int i = mr + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
-            __syncthreads();
-            block_bitonic_sort(skeys, P, tid);
-            bpos = e;
-            consumed = mr;
-            m = mr < (n_proc - processed) ? mr : (n_proc - processed);  // max_nms cut inside the round
         } else {
-            // radix select: T = m-th smallest key among keys > lo (8 passes of 8 bits, MSD first)
-            unsigned long long prefix = 0, pmask = 0;
-            int remaining = m;
-            for (int pass = 0; pass < 8; ++pass) {
-                const int shift = 56 - 8 * pass;
-                if (tid < 256) hist[tid] = 0;
+            bool staged = false;
+            if (use_bins) {
+                // the best ~kRoundTarget unconsumed candidates: bins [bpos, e)
+                if (tid == 0) {
+                    const uint32_t base = bpos ? cum[bpos - 1] : 0u;
+                    int lo_b = bpos, hi_b = kBins - 1;  // smallest e-1 with cum[e-1] - base >= target (or last bin)
+                    while (lo_b < hi_b) {
+                        const int mid = (lo_b + hi_b) >> 1;
+                        if (cum[mid] - base >= (uint32_t)kRoundTarget) hi_b = mid; else lo_b = mid + 1;
+                    }
+                    misc[0] = lo_b + 1;
+                    misc[1] = (int)(cum[lo_b] - base);
+                    misc[2] = 0;
+                }
+                __syncthreads();
+                const int e = misc[0];
+                const int mr = misc[1];
+                if (mr <= kBinRoundMax) {
+                    for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+                        const int i = i0 + tid;
+                        unsigned long long k = 0;
+                        bool take = false;
+                        if (i < n) {
+                            k = gkeys[i];
+                            const int kb = key_bin(k);
+                            take = kb >= bpos && kb < e;
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, take);
+                        if (bal) {
+                            int pos0 = 0;
+                            if (lane == 0) pos0 = atomicAdd(&misc[2], __popc(bal));
+                            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                            if (take) skeys[pos0 + __popc(bal & ((1u << lane) - 1u))] = k;
+                        }
+                    }
+                    __syncthreads();
+                    int P = 32;
+                    while (P < mr) P <<= 1;
+                    for (int i = mr + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
+                    __syncthreads();
+                    block_bitonic_sort(skeys, P, tid);
+                    bpos = e;
+                    lo = skeys[mr - 1];  // largest key consumed so far (a later radix round resumes above it)
+                    consumed = mr;
+                    m = mr < (n_proc - processed) ? mr : (n_proc - processed);  // max_nms cut inside the round
+                    staged = true;
+                } else {
+                    // the score bins are too coarse here (many near-equal scores): exact radix rounds from now on;
+                    // every key of the bins consumed so far is <= lo, every other key is > lo
+                    use_bins = false;
+                    __syncthreads();  // misc[] is rewritten below
+                }
+            }
+            if (!staged) {
+                // radix select: T = m-th smallest key among keys > lo (8 passes of 8 bits, MSD first); a round takes
+                // the next kRoundTarget candidates, so a greedy scan that fills max_det early never sorts the rest
+                if (m > kRoundTarget) m = kRoundTarget;
+                consumed = m;
+                unsigned long long prefix = 0, pmask = 0;
+                int remaining = m;
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int shift = 56 - 8 * pass;
+                    if (tid < 256) hist[tid] = 0;
+                    __syncthreads();
+                    for (int i = tid; i < n; i += kSelThreads) {
+                        const unsigned long long k = gkeys[i];
+                        if (k > lo && (k & pmask) == prefix) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xffu], 1u);
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        // digit d with count(digits < d) < remaining <= count(digits <= d): 8 bins per lane
+                        uint32_t c[8], ls = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            c[i] = hist[lane * 8 + i];
+                            ls += c[i];
+                        }
+                        uint32_t incl = ls;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        const unsigned hit = __ballot_sync(0xffffffffu, incl >= (uint32_t)remaining);
+                        const int src = hit ? (__ffs(hit) - 1) : 31;
+                        if (lane == src) {
+                            uint32_t acc = incl - ls;
+                            int d = 0;
+                            for (; d < 7; ++d) {
+                                if (acc + c[d] >= (uint32_t)remaining) break;
+                                acc += c[d];
+                            }
+                            misc[0] = lane * 8 + d;
+                            misc[1] = remaining - (int)acc;
+                        }
+                    }
+                    __syncthreads();
+                    prefix |= (unsigned long long)misc[0] << shift;
+                    pmask |= 0xffull << shift;
+                    remaining = misc[1];
+                    __syncthreads();
+                }
+                const unsigned long long T = prefix;
+                if (tid == 0) misc[2] = 0;
                 __syncthreads();
                 for (int i = tid; i < n; i += kSelThreads) {
                     const unsigned long long k = gkeys[i];
-                    if (k > lo && (k & pmask) == prefix) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xffu], 1u);
+                    if (k > lo && k <= T) skeys[atomicAdd(&misc[2], 1)] = k;
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int acc = 0, d = 0;
-                    for (; d < 256; ++d) {
-                        const int c = (int)hist[d];
-                        if (acc + c >= remaining) break;
-                        acc += c;
-                    }
-                    misc[0] = d;
-                    misc[1] = remaining - acc;
-                }
+                // exactly m keys were gathered (keys are unique); sort them
+                int P = 32;
+                while (P < m) P <<= 1;
+                for (int i = m + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
                 __syncthreads();
-                prefix |= (unsigned long long)misc[0] << shift;
-                pmask |= 0xffull << shift;
-                remaining = misc[1];
-                __syncthreads();
+                block_bitonic_sort(skeys, P, tid);
+                lo = T;
             }
-            const unsigned long long T = prefix;
-            if (tid == 0) misc[2] = 0;
-            __syncthreads();
-            for (int i = tid; i < n; i += kSelThreads) {
-                const unsigned long long k = gkeys[i];
-                if (k > lo && k <= T) skeys[atomicAdd(&misc[2], 1)] = k;
-            }
-            __syncthreads();
-            // exactly m keys were gathered (keys are unique); sort them
-            int P = 32;
-            while (P < m) P <<= 1;
-            for (int i = m + tid; i < P; i += kSelThreads) skeys[i] = ~0ull;
-            __syncthreads();
-            block_bitonic_sort(skeys, P, tid);
-            lo = T;
         }
 
         // ---------------- greedy suppression over skeys[0..m) in chunks

@@ -29,6 +29,8 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
 
 __global__ void __launch_bounds__(256) sppf_pool_kernel(const PoolParams p) {
     extern __shared__ __align__(16) uint4 plane[];  // [2][H*W]
+    griddep_launch_dependents();
+    griddep_wait();
     const int HW = p.H * p.W;
     uint4* cur = plane;
     uint4* tmp = plane + HW;
@@ -99,7 +101,7 @@ extern "C" int yl_sppf_pool(const yl_tensor* x, const yl_tensor* y1, const yl_te
              "SPPF plane %dx%d needs %zu B shared memory (max %d; yl_init called?)", x->h, x->w, smem,
              yl::g_pool_max_smem);
     dim3 grid((unsigned)(x->c / 8), (unsigned)x->n, 1);
-    yl::sppf_pool_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    YL_CUDA(yl::launch_kernel(yl::sppf_pool_kernel, grid, dim3(256), smem, (cudaStream_t)stream, p));
     YL_LAUNCH_OK("sppf_pool_kernel");
     return YL_OK;
 }

@@ -1,6 +1,7 @@
 // yl11 runtime: error text, device binding, driver entry point for the TMA descriptor encoder.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,6 +25,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 EncodeTiledFn get_encode_tiled() { return g_encode; }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("YL_PDL");
+        v = (e && *e) ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
 
 int init_conv_tc();    // conv_tc.cu
 int init_nms();        // nms.cu

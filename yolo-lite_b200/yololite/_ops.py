@@ -90,7 +90,7 @@ def pack_conv(weight: torch.Tensor, bn=None, conv_bias=None, device=None) -> Pac
         gamma = beta = mean = var = None
         eps = 0.0
     cb = _f32(conv_bias, dev)
-    co_pad = round_up(co, 16)
+    co_pad = round_up(co, 8) if depthwise else round_up(co, 16)   # yl_dwconv3x3 takes w as [9][c], c % 8 == 0
     ci_pad = 1 if depthwise else round_up(cig, 8)
     if depthwise:
         wp = torch.empty((k * k, co_pad), dtype=torch.bfloat16, device=dev)
@@ -130,6 +130,15 @@ def conv(x: View, y: View, pc: PackedConv, stride=1, act=True, res=None, upsampl
         return
     a = conv_args(x, y, pc, stride, act, res, upsample, impl, y_up)
     _C.check(lib.yl_conv_bn_act(C.byref(a), _C.stream_ptr()), "yl_conv_bn_act")
+
+
+def stem_conv(x_nchw: torch.Tensor, y: View, pc: PackedConv, act=True):
+    """Fused ingest + first layer: NCHW fp32 CUDA batch (<= 4 channels) -> 3x3 s2 conv + folded BN + SiLU -> NHWC bf16."""
+    assert x_nchw.is_cuda and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and x_nchw.dim() == 4
+    n, c, h, w = x_nchw.shape
+    yt = y.ct()
+    _C.check(_C.load().yl_stem_conv(x_nchw.data_ptr(), n, c, h, w, pc.w.data_ptr(), pc.ci_pad, pc.bias.data_ptr(),
+                                    C.byref(yt), int(act), _C.stream_ptr()), "yl_stem_conv")
 
 
 def sppf_pool(x: View, y1: View, y2: View, y3: View, k=5):

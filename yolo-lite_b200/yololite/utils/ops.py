@@ -117,7 +117,7 @@ def convert_torch2numpy_batch(batch: torch.Tensor) -> np.ndarray:
 
 
 def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-               max_det=300, nc=0, max_nms=30000, max_wh=7680):
+               max_det=300, nc=0, max_nms=30000, max_wh=7680, out=None, counts=None):
     """Device-resident NMS: (B, 4+nc, A) -> (dets (B, max_det, 6) fp32, counts (B,) int32), fully async.
 
     This is what the engine uses; `non_max_suppression` below turns it into the reference's list layout."""
@@ -130,7 +130,8 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
         raise NotImplementedError("mask coefficients (nm > 0) are outside the detection path")
     pred = prediction if (prediction.dtype == torch.float32 and prediction.is_contiguous()) else \
         prediction.float().contiguous()
-    return _ops.nms_batched(pred, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    return _ops.nms_batched(pred, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh,
+                            out=out, counts=counts)
 
 
 def non_max_suppression(
