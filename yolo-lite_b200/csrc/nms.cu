@@ -18,6 +18,7 @@
 // IoU arithmetic follows torchvision's CPU kernel operation by operation (no FMA contraction, same
 // std::max/std::min operand order, fp32 IoU compared against the double threshold).
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -147,6 +148,8 @@ struct SelParams {
     const uint32_t* counts;
     const unsigned long long* keys;
     float thr;           // largest float <= double iou threshold
+    double thr_mid;      // midpoint of thr and the next float above it (exact in double)
+    int thr_tie_up;      // a quotient exactly at thr_mid rounds (ties-to-even) to the float ABOVE thr
     float max_wh;        // class offset scale (0 when agnostic)
     int max_det, max_nms;
     int kept_in_smem;
@@ -157,8 +160,17 @@ struct SelParams {
     long long* keep;     // MODE 1: int64[n]
 };
 
-// torchvision CPU: suppressed iff inter / (area_i + area_j - inter) > thr, i = kept (earlier) box.
-__device__ __forceinline__ bool iou_suppresses(const float4 bi, float ai, const float4 bj, float aj, float thr) {
+// torchvision CPU: suppressed iff inter / (area_i + area_j - inter) > thr, i = kept (earlier) box; every
+// operation is an individually rounded fp32 op (no FMA contraction), the quotient is correctly rounded.
+// The division itself is avoided: with t+ the float after thr and mid = (thr + t+) / 2,
+//     RN(inter / uni) > thr  <=>  RN(inter / uni) >= t+  <=>  inter / uni > mid  (or == mid when the tie rounds up)
+// and for uni > 0 that is inter > mid * uni, which is exact in double (25-bit x 24-bit significands).
+struct IouThr {
+    float thr;
+    double mid;
+    int tie_up;
+};
+__device__ __forceinline__ bool iou_suppresses(const float4 bi, float ai, const float4 bj, float aj, const IouThr t) {
     const float xx1 = (bi.x < bj.x) ? bj.x : bi.x;  // std::max(ix1, x1[j])
     const float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
     const float xx2 = (bj.z < bi.z) ? bj.z : bi.z;  // std::min(ix2, x2[j])
@@ -168,11 +180,13 @@ __device__ __forceinline__ bool iou_suppresses(const float4 bi, float ai, const 
     const float h = (0.f < dh) ? dh : 0.f;
     const float inter = __fmul_rn(w, h);
     // disjoint boxes (the common case once classes are offset apart): inter == +0, so ovr is 0 or NaN (0/0) and
-    // `ovr > thr` is false for every thr >= 0 -- skip the IEEE division.  A NaN inter fails this test and takes
-    // the division like the reference does.
+    // `ovr > thr` is false for every thr >= 0.  A NaN inter fails this test and takes the division below.
     if (inter == 0.f) return false;
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
-    return ovr > thr;
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    if (!(inter > 0.f) || !(uni > 0.f) || isinf(inter) || isinf(uni))
+        return __fdiv_rn(inter, uni) > t.thr;  // NaN / inf / non-positive union: the reference's own arithmetic
+    const double lhs = (double)inter, rhs = t.mid * (double)uni;
+    return t.tie_up ? (lhs >= rhs) : (lhs > rhs);
 }
 
 template <int MODE>
@@ -445,24 +459,29 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
         }
 
         // ---------------- greedy suppression over skeys[0..m) in chunks
+        const IouThr thr = {p.thr, p.thr_mid, p.thr_tie_up};
         for (int s0 = 0; s0 < m && nk < p.max_det; s0 += kChunk) {
             const int cnt = (m - s0) < kChunk ? (m - s0) : kChunk;
-            // 1. candidate vs kept list
+            // 1. candidate vs kept list: two threads per candidate, each scanning every other kept box
+            const int ci = tid >> 1, half = tid & 1;
             float4 ob = make_float4(0, 0, 0, 0), rb;
             float ar = 0.f, sc;
             int cl;
             bool alive = false;
-            if (tid < cnt) {
-                fetch_box<MODE>(p, b, skeys[s0 + tid], &rb, &ob, &ar, &sc, &cl);
+            if (ci < cnt) {
+                fetch_box<MODE>(p, b, skeys[s0 + ci], &rb, &ob, &ar, &sc, &cl);
                 alive = true;
-                for (int i = 0; i < nk; ++i) {
+                for (int i = half; i < nk; i += 2) {
                     const float4 kb = make_float4(kept[i * 5 + 0], kept[i * 5 + 1], kept[i * 5 + 2], kept[i * 5 + 3]);
-                    if (iou_suppresses(kb, kept[i * 5 + 4], ob, ar, p.thr)) {
+                    if (iou_suppresses(kb, kept[i * 5 + 4], ob, ar, thr)) {
                         alive = false;
                         break;
                     }
                 }
             }
+            // (the shuffle must be executed by every lane: no short-circuit in front of it)
+            const int other_alive = __shfl_xor_sync(0xffffffffu, (int)alive, 1);
+            alive = alive && other_alive && (half == 0);  // the even thread of the pair carries the candidate on
             // 2. ordered compaction of survivors
             const unsigned bal = __ballot_sync(0xffffffffu, alive);
             if (lane == 0) misc[8 + warp] = __popc(bal);
@@ -483,57 +502,77 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
                 const int pos = misc[8 + warp] + __popc(bal & ((1u << lane) - 1u));
                 cbox[pos] = ob;
                 carea[pos] = ar;
-                csrc[pos] = s0 + tid;
+                csrc[pos] = s0 + ci;
             }
             __syncthreads();
-            // 3. pairwise bitmask among survivors (upper triangle)
+            // 3. pairwise bitmask among survivors: only the words on or right of the diagonal exist.  Row block
+            //    rbk (rows 32*rbk ..) has W - rbk words per row; the work items are flattened over them.
             const int W = (L + 31) >> 5;
-            for (int e = tid; e < L * W; e += kSelThreads) {
-                const int i = e / W, wd = e - i * W;
-                uint32_t bits = 0;
-                if (wd >= (i >> 5)) {
+            {
+                int total = 0;
+                for (int rbk = 0; rbk < W; ++rbk) total += min(32, L - 32 * rbk) * (W - rbk);
+                for (int e = tid; e < total; e += kSelThreads) {
+                    int rem_e = e, rbk = 0;
+                    for (;; ++rbk) {
+                        const int c = min(32, L - 32 * rbk) * (W - rbk);
+                        if (rem_e < c) break;
+                        rem_e -= c;
+                    }
+                    const int per_row = W - rbk;
+                    const int i = rbk * 32 + rem_e / per_row;
+                    const int wd = rbk + rem_e % per_row;
                     const float4 bi = cbox[i];
                     const float ai = carea[i];
                     const int j0 = wd << 5;
+                    uint32_t bits = 0;
                     for (int jj = 0; jj < 32; ++jj) {
                         const int j = j0 + jj;
-                        if (j > i && j < L && iou_suppresses(bi, ai, cbox[j], carea[j], p.thr)) bits |= 1u << jj;
+                        if (j > i && j < L && iou_suppresses(bi, ai, cbox[j], carea[j], thr)) bits |= 1u << jj;
                     }
+                    mask[i * kMaskWords + wd] = bits;
                 }
-                mask[i * kMaskWords + wd] = bits;
             }
             __syncthreads();
-            // 4. serial resolve by warp 0: lane l owns word l of the removed set
+            // 4. resolve by warp 0, one block of 32 candidates at a time: the 32 x 32 diagonal block is resolved
+            //    with register shuffles only (lane l holds row l's diagonal word), then the kept rows are OR-ed into
+            //    the removed set (lane w owns word w) and appended to the kept list in parallel.
             if (warp == 0) {
                 uint32_t rem = 0;
-                int cur = 0;
                 int nk_l = nk;
-                while (nk_l < p.max_det) {
-                    // first index >= cur that is valid and not removed
-                    uint32_t cand = 0;
-                    if (lane < W) {
-                        cand = ~rem;
-                        const int lo_i = lane << 5;
-                        if (L - lo_i < 32) cand &= (L - lo_i <= 0) ? 0u : ((1u << (L - lo_i)) - 1u);
-                        if (cur > lo_i) cand &= (cur - lo_i >= 32) ? 0u : ~((1u << (cur - lo_i)) - 1u);
+                for (int blk = 0; blk < W && nk_l < p.max_det; ++blk) {
+                    const int r = blk * 32 + lane;
+                    const uint32_t diag = (r < L) ? mask[r * kMaskWords + blk] : 0u;
+                    const int nrows = L - blk * 32;
+                    const uint32_t vm = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
+                    uint32_t live = ~__shfl_sync(0xffffffffu, rem, blk) & vm;
+                    uint32_t keepbits = 0;
+                    int room = p.max_det - nk_l;
+                    while (live && room > 0) {
+                        const int l = __ffs(live) - 1;
+                        keepbits |= 1u << l;
+                        --room;
+                        live &= ~(__shfl_sync(0xffffffffu, diag, l) | (1u << l));
                     }
-                    const unsigned has = __ballot_sync(0xffffffffu, cand != 0);
-                    if (!has) break;
-                    const int src_lane = __ffs(has) - 1;
-                    const uint32_t cw = __shfl_sync(0xffffffffu, cand, src_lane);
-                    const int i = (src_lane << 5) + (__ffs(cw) - 1);
-                    if (lane < W) rem |= mask[i * kMaskWords + lane];
-                    if (lane == 0) {
-                        const float4 bb = cbox[i];
-                        kept[nk_l * 5 + 0] = bb.x;
-                        kept[nk_l * 5 + 1] = bb.y;
-                        kept[nk_l * 5 + 2] = bb.z;
-                        kept[nk_l * 5 + 3] = bb.w;
-                        kept[nk_l * 5 + 4] = carea[i];
-                        kept_keys[nk_l] = skeys[csrc[i]];
+                    // removed set of the later blocks
+                    if (lane > blk && lane < W) {
+                        uint32_t kb = keepbits;
+                        while (kb) {
+                            const int l = __ffs(kb) - 1;
+                            kb &= kb - 1;
+                            rem |= mask[(blk * 32 + l) * kMaskWords + lane];
+                        }
                     }
-                    ++nk_l;
-                    cur = i + 1;
+                    if ((keepbits >> lane) & 1u) {
+                        const int pos = nk_l + __popc(keepbits & ((1u << lane) - 1u));
+                        const float4 bb = cbox[r];
+                        kept[pos * 5 + 0] = bb.x;
+                        kept[pos * 5 + 1] = bb.y;
+                        kept[pos * 5 + 2] = bb.z;
+                        kept[pos * 5 + 3] = bb.w;
+                        kept[pos * 5 + 4] = carea[r];
+                        kept_keys[pos] = skeys[csrc[r]];
+                    }
+                    nk_l += __popc(keepbits);
                 }
                 if (lane == 0) misc[4] = nk_l;
             }
@@ -590,6 +629,16 @@ static float thr_to_float(double thr) {
     float f = (float)thr;
     if ((double)f > thr) f = nextafterf(f, -INFINITY);
     return f;
+}
+
+// Rounding boundary between thr and the next float above it, and which way an exact tie goes (round-to-nearest-
+// even picks the neighbour with an even significand: the upper one iff thr's is odd).
+static void thr_midpoint(float thr, double* mid, int* tie_up) {
+    const float up = nextafterf(thr, INFINITY);
+    *mid = ((double)thr + (double)up) * 0.5;  // exact: both are floats one ulp apart
+    uint32_t bits;
+    memcpy(&bits, &thr, 4);
+    *tie_up = (int)(bits & 1u);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -681,6 +730,7 @@ int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, do
     p.counts = cand_counts;
     p.keys = keys;
     p.thr = yl::thr_to_float(iou_thres);
+    yl::thr_midpoint(p.thr, &p.thr_mid, &p.thr_tie_up);
     p.max_wh = agnostic ? 0.f : max_wh;
     p.max_det = max_det;
     p.max_nms = max_nms;
@@ -733,6 +783,7 @@ int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thre
     p.counts = cand_counts;
     p.keys = keys;
     p.thr = yl::thr_to_float(iou_thres);
+    yl::thr_midpoint(p.thr, &p.thr_mid, &p.thr_tie_up);
     p.max_wh = 0.f;
     p.max_det = n;
     p.max_nms = n;
