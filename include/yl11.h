@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define YL11_VERSION 101
+#define YL11_VERSION 102
 
 typedef enum yl_status {
     YL_OK = 0,
@@ -84,6 +84,24 @@ int yl_upsample2x(const yl_tensor* x, const yl_tensor* y, void* stream);
  * `y.h/y.w` are the conv output dims; with upsample2x != 0 each result pixel is replicated into the 2x2
  * block of a (n, 2h, 2w) buffer described by `y` (then y.h/y.w are the *upsampled* dims).
  * The tcgen05 path stores through TMA: out-of-range rows/channels are clipped by the tensor map. */
+/* Optional Detect-decode epilogue of a 1x1 head conv (head.py:95-126 fused into the conv that produces the
+ * logits, so the raw head map need not be written and re-read): the conv result (+bias, no activation) of
+ * pixel (b, a_local) is decoded straight into the prediction tensor pred (B, 4+nc, A) fp32:
+ *   mode YL_DET_BOX  (co == 4*reg_max, reg_max == 16): DFL softmax-expectation per side (block.py:51-69),
+ *        dist2bbox around the anchor centre (tal.py:341-350), * stride  -> pred[b, 0:4, anchor0 + a_local]
+ *   mode YL_DET_CLS  (co == nc): sigmoid                               -> pred[b, 4:4+nc, anchor0 + a_local]
+ * With det.pred != NULL the NHWC destination `y` becomes optional (y.data may be NULL: no raw map at all). */
+typedef enum yl_det_mode { YL_DET_NONE = 0, YL_DET_BOX = 1, YL_DET_CLS = 2 } yl_det_mode;
+typedef struct yl_det_epilogue {
+    float* pred;     /* NULL: plain conv epilogue */
+    int32_t mode;    /* yl_det_mode */
+    int32_t reg_max; /* 16 */
+    int32_t nc;      /* classes: pred has 4 + nc rows */
+    int32_t A;       /* anchors per image over all levels */
+    int32_t anchor0; /* first anchor of this level */
+    float stride;    /* level stride in pixels */
+} yl_det_epilogue;
+
 typedef struct yl_conv_args {
     yl_tensor x;
     yl_tensor y;   /* bf16 or f32 */
@@ -99,6 +117,7 @@ typedef struct yl_conv_args {
     int32_t upsample2x;
     int32_t impl;           /* yl_conv_impl                                                   */
     int32_t _pad;
+    yl_det_epilogue det;    /* det.pred == NULL: none (tcgen05 path only, k = 1, stride 1, no act/res) */
 } yl_conv_args;
 int yl_conv_bn_act(const yl_conv_args* a, void* stream);
 /* 1 if the tcgen05 implicit-GEMM path can run this problem, 0 if it needs the direct kernel. */

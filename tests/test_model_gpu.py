@@ -174,3 +174,52 @@ def test_checkpoint_roundtrip_pt(tmp_path, golden):
     x = torch.from_numpy(g["x"])
     y, _ = yl.model.cuda().eval()(x.cuda())
     assert np.abs(y.cpu().numpy()[:, 4:] - g["y"][:, 4:]).max() <= SCORE_TOL
+
+
+def test_fused_decode_matches_decode_kernel_and_engine_path(golden):
+    """The Detect decode fused into the head convs' epilogue (a) equals the standalone decode kernel fed by the
+    raw maps within fp32 rounding of the fast exp, (b) is identical with and without materialising the raw maps
+    (engine path `infer(want_raw=False)`), also for a batch that leaves the last 128-pixel tile ragged."""
+    from yololite.nn.modules import Detect
+    from yololite.nn.tasks import DetectionModel
+
+    g = golden("model_yolo11n.npz")
+    sd = model_state_dict(g)
+    x = torch.rand(3, 3, 96, 160, generator=torch.Generator().manual_seed(5)).cuda()   # P5 map: 3*3*5 = 45 pixels
+    outs = {}
+    for fuse in (True, False):
+        Detect.fuse_decode = fuse
+        try:
+            m = DetectionModel("yolo11n.yaml", verbose=False)
+            m.load_state_dict(sd)
+            m = m.cuda().eval()
+            y, raw = m(x)
+            outs[fuse] = (y.cpu().numpy(), [r.cpu().numpy() for r in raw])
+            if fuse:
+                y_engine, no_raw = m.infer(x)           # want_raw=False: separate plan, no raw maps written
+                assert no_raw == []
+                np.testing.assert_array_equal(y_engine.cpu().numpy(), outs[True][0])
+        finally:
+            Detect.fuse_decode = True
+    (yf, rf), (yk, rk) = outs[True], outs[False]
+    for a, b in zip(rf, rk):
+        np.testing.assert_array_equal(a, b)              # same conv, same raw logits
+    assert np.abs(yf[:, :4] - yk[:, :4]).max() <= 2e-3   # box px: __expf / __fdividef vs expf / div
+    assert np.abs(yf[:, 4:] - yk[:, 4:]).max() <= 1e-5
+
+
+def test_predict_pipelined_host_batch_equals_device_batch(golden):
+    """A pinned HOST batch goes through the chunk-pipelined ingest (4 chunks of 8); the detections must be the
+    same as for the same batch already resident on the device (single plan, no chunking)."""
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    x = torch.rand(32, 3, 64, 96, generator=torch.Generator().manual_seed(2))
+    r_host = yl.predict(x.pin_memory(), conf=0.05, verbose=False)
+    assert yl.predictor._chunking(x) == 4
+    r_dev = yl.predict(x.cuda(), conf=0.05, verbose=False)
+    assert len(r_host) == len(r_dev) == 32
+    for a, b in zip(r_host, r_dev):
+        assert torch.equal(a.boxes.data, b.boxes.data)

@@ -18,7 +18,7 @@ int yl_conv_tc_supported(const yl_conv_args* a) {
 
 int yl_conv_bn_act(const yl_conv_args* a, void* stream) {
     YL_CHECK(a != nullptr, YL_ERR_ARG, "null conv args");
-    YL_CHECK(a->x.data && a->y.data && a->w && a->bias, YL_ERR_ARG, "null tensor pointer");
+    YL_CHECK(a->x.data && (a->y.data || a->det.pred) && a->w && a->bias, YL_ERR_ARG, "null tensor pointer");
     YL_CHECK(a->x.c > 0 && a->y.c > 0 && a->x.n > 0 && a->x.h > 0 && a->x.w > 0, YL_ERR_ARG, "empty tensor");
     YL_CHECK(a->x.coff + a->x.c <= a->x.cstride && a->y.coff + a->y.c <= a->y.cstride, YL_ERR_ARG,
              "channel slice exceeds buffer");
@@ -26,6 +26,10 @@ int yl_conv_bn_act(const yl_conv_args* a, void* stream) {
         YL_CHECK(a->res.c == a->y.c && a->res.coff + a->res.c <= a->res.cstride, YL_ERR_ARG, "residual slice mismatch");
     }
     cudaStream_t s = (cudaStream_t)stream;
+    if (a->det.pred) {
+        YL_CHECK(a->impl != YL_IMPL_DIRECT, YL_ERR_UNSUPPORTED, "the Detect-decode epilogue exists on the tcgen05 path only");
+        return yl::launch_conv_tc(a, s);
+    }
     if (a->impl == YL_IMPL_DIRECT) return yl::launch_conv_direct(a, s);
     if (a->impl == YL_IMPL_TCGEN05) return yl::launch_conv_tc(a, s);
     if (yl::conv_tc_supported(a, nullptr, 0)) return yl::launch_conv_tc(a, s);

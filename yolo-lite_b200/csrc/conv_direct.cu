@@ -389,12 +389,13 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
 // writes NHWC bf16.  Replaces a layout pass (read 4.9 MB + write 2.5 MB per image) plus a conv pass with one
 // kernel whose traffic is the algorithmic minimum (read image once, write activations once).
 //
-// The GEMM is M = pixels, N = CO, K = 9*Ci (27 -> padded to 32): too thin for tcgen05 (no TMA im2col of an
-// fp32 NCHW image), but a CUDA-core kernel is FMA/LDS-issue bound at ~4x the HBM time.  So the im2col A
-// fragments are gathered straight into registers (k = tap*Ci + ci, rounded to bf16 exactly like the NHWC
-// ingest would) and multiplied with warp-level mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  A warp walks 64
-// consecutive output pixels of one row in four 16-pixel steps; the weight (B) fragments and biases stay in
-// registers for the whole walk.
+// The GEMM is M = pixels, N = CO, K = 9 taps x 4 (channel-padded) = 36: too thin for tcgen05 (no TMA im2col of
+// an fp32 NCHW image), but a CUDA-core kernel is FMA/LDS-issue bound at ~4x the HBM time.  A block stages the
+// 17 x 132-pixel input patch of its 8 x 64 output tile in shared memory with coalesced 16-byte loads, rounded
+// to bf16 exactly like the NHWC ingest would and interleaved [row][col][4 ch], so every k-pair of an im2col
+// row is one conflict-free 32-bit shared load straight into an mma.sync.m16n8k16 A fragment (bf16 x bf16 ->
+// fp32).  A warp walks the 64 output pixels of one row in four 16-pixel steps; the weight (B) fragments and
+// biases stay in registers for the whole walk.
 namespace yl {
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -406,42 +407,29 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 constexpr int kStemRowPixels = 64;  // output pixels of one row per warp
 constexpr int kStemWarps = 8;       // output rows per block
+// input patch of a block: rows 2*h0-1 .. 2*h0+15, columns 2*w0-4 .. 2*w0+127 (16-byte aligned start), staged in
+// shared memory as bf16 pixel-interleaved [row][col][4 channels] so a k-pair of the im2col row is one 32-bit word
+constexpr int kStemPatchRows = 2 * kStemWarps + 1;
+constexpr int kStemPatchCols = 2 * kStemRowPixels + 4;
 
-template <int CO, int KSTEPS>
+// K order: k = tap * 4 + ci (ci padded to 4), K = 36 -> 3 k-steps of 16.
+template <int CO, int CI>
 __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
-    const float* __restrict__ x, int N, int Ci, int H, int W, const __nv_bfloat16* __restrict__ wp, int ci_pad,
+    const float* __restrict__ x, int N, int H, int W, const __nv_bfloat16* __restrict__ wp, int ci_pad,
     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long y_cstride, int y_coff, int Ho, int Wo,
     int act) {
     constexpr int NT = CO / 8;
-    constexpr int NSLOT = KSTEPS * 4;
+    constexpr int KSTEPS = 3;
+    constexpr int Ci = CI;
+    __shared__ __align__(16) uint2 patch[kStemPatchRows * kStemPatchCols];  // one pixel = 4 x bf16 = 8 bytes
     griddep_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int ho = blockIdx.y * kStemWarps + warp;
+    const int h0 = blockIdx.y * kStemWarps;
+    const int w0 = blockIdx.x * kStemRowPixels;
     const int n = blockIdx.z;
-    const int wbase = blockIdx.x * kStemRowPixels;
-    if (ho >= Ho) return;
-    const int K = 9 * Ci;
     const long long plane = (long long)H * W;
 
-    // k slots of this thread (fragment layout of mma.m16n8k16: k = 16*ks + {2t, 2t+1, 2t+8, 2t+9})
-    int off[NSLOT];                       // element offset of the slot's tap/channel from (n, 0, 2ho, 2wo)
-    uint32_t m_valid = 0, m_top = 0, m_left = 0, m_bot = 0, m_right = 0;
-#pragma unroll
-    for (int i = 0; i < NSLOT; ++i) {
-        const int k = 16 * (i >> 2) + 2 * t + (i & 1) + ((i >> 1) & 1) * 8;
-        const int tap = k / Ci, ci = k - tap * Ci;
-        const int r = tap / 3, s2 = tap - 3 * r;
-        off[i] = 0;
-        if (k < K) {
-            off[i] = (int)(ci * plane) + (r - 1) * W + (s2 - 1);
-            m_valid |= 1u << i;
-            if (r == 0) m_top |= 1u << i;
-            if (r == 2) m_bot |= 1u << i;
-            if (s2 == 0) m_left |= 1u << i;
-            if (s2 == 2) m_right |= 1u << i;
-        }
-    }
     // B fragments: b0 = {W[k0][n], W[k0+1][n]}, b1 = {W[k0+8][n], W[k0+9][n]}, k0 = 16*ks + 2t, n = 8*nt + g
     uint32_t bfrag[KSTEPS][NT][2];
     float bia[NT][2];
@@ -457,11 +445,9 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int k = 16 * ks + 2 * t + e + hh * 8;
+                    const int tap = k >> 2, ci = k & 3;
                     uint32_t bits = 0;
-                    if (k < K) {
-                        const int tap = k / Ci, ci = k - tap * Ci;
-                        bits = (uint32_t)__bfloat16_as_ushort(wrow[tap * ci_pad + ci]);
-                    }
+                    if (tap < 9 && ci < Ci) bits = (uint32_t)__bfloat16_as_ushort(wrow[tap * ci_pad + ci]);
                     v |= bits << (16 * e);
                 }
                 bfrag[ks][nt][hh] = v;
@@ -471,32 +457,77 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
     }
     griddep_wait();
 
-    const float* xrow = x + (long long)n * Ci * plane + (long long)(2 * ho) * W;
-    uint32_t m_row = m_valid;
-    if (ho == 0) m_row &= ~m_top;
-    if (2 * ho + 1 >= H) m_row &= ~m_bot;
+    // ---- stage the patch: a work item = 4 consecutive columns of one patch row, all channels (coalesced 16-B
+    // loads per channel plane when W % 4 == 0, scalar otherwise), rounded to bf16 exactly like an NHWC ingest
+    const float* xn = x + (long long)n * Ci * plane;
+    const bool vec_ok = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    constexpr int kQuads = kStemPatchCols / 4;
+    for (int item = threadIdx.x; item < kStemPatchRows * kQuads; item += 32 * kStemWarps) {
+        const int pr = item / kQuads, q = item - pr * kQuads;
+        const int hi = 2 * h0 - 1 + pr;
+        const int wi0 = 2 * w0 - 4 + 4 * q;
+        float v[4][4];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[ci][e] = 0.f;
+        if (hi >= 0 && hi < H) {
+            const float* src0 = xn + (long long)hi * W + wi0;
+            if (vec_ok && wi0 >= 0 && wi0 + 3 < W) {
+                float4 f[CI];
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) f[ci] = __ldg(reinterpret_cast<const float4*>(src0 + ci * plane));
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    v[ci][0] = f[ci].x; v[ci][1] = f[ci].y; v[ci][2] = f[ci].z; v[ci][3] = f[ci].w;
+                }
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (wi0 + e >= 0 && wi0 + e < W) v[ci][e] = __ldg(src0 + ci * plane + e);
+            }
+        }
+        // 4 pixels x 8 bytes = two 16-byte shared stores
+        uint4* dst = reinterpret_cast<uint4*>(patch + pr * kStemPatchCols + 4 * q);
+        dst[0] = make_uint4(pack_bf16x2(v[0][0], v[1][0]), pack_bf16x2(v[2][0], v[3][0]),
+                            pack_bf16x2(v[0][1], v[1][1]), pack_bf16x2(v[2][1], v[3][1]));
+        dst[1] = make_uint4(pack_bf16x2(v[0][2], v[1][2]), pack_bf16x2(v[2][2], v[3][2]),
+                            pack_bf16x2(v[0][3], v[1][3]), pack_bf16x2(v[2][3], v[3][3]));
+    }
+    __syncthreads();
+
+    const int ho = h0 + warp;
+    if (ho >= Ho) return;
+    // fragment word offsets (in 32-bit words) of this thread's k slots relative to patch pixel (2*warp, 2*wl + 3):
+    // k = 16*ks + 2t (+8): tap = k / 4 -> (r, s), channel pair = (k / 2) & 1
+    int woff[KSTEPS][2];
+    bool kval[KSTEPS][2];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int k = 16 * ks + 2 * t + hh * 8;
+            const int tap = k >> 2, r = tap / 3, s2 = tap - 3 * r;
+            kval[ks][hh] = tap < 9;
+            woff[ks][hh] = kval[ks][hh] ? ((r * kStemPatchCols + s2) * 2 + ((k >> 1) & 1)) : 0;
+        }
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(patch) + (2 * warp * kStemPatchCols + 3) * 2;
     __nv_bfloat16* yrow = y + ((long long)n * Ho + ho) * Wo * y_cstride + y_coff;
 
 #pragma unroll 1
     for (int mt = 0; mt < kStemRowPixels / 16; ++mt) {
-        const int wo0 = wbase + mt * 16;
-        if (wo0 >= Wo) break;
+        const int wl0 = mt * 16;
+        if (w0 + wl0 >= Wo) break;
         uint32_t a[KSTEPS][4];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {      // fragment rows g and g + 8
-            const int wo = wo0 + g + half * 8;
-            uint32_t m = (wo < Wo) ? m_row : 0u;
-            if (wo == 0) m &= ~m_left;
-            if (2 * wo + 1 >= W) m &= ~m_right;
-            const float* px = xrow + 2 * wo;
-            float v[NSLOT];
-#pragma unroll
-            for (int i = 0; i < NSLOT; ++i) v[i] = ((m >> i) & 1u) ? __ldg(px + off[i]) : 0.f;
+            const uint32_t* px = pw + (wl0 + g + half * 8) * 4;  // 2 input columns per output pixel, 2 words each
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
-                // a0/a1: k = 2t, 2t+1 (rows g / g+8);  a2/a3: k = 2t+8, 2t+9
-                a[ks][half] = pack_bf16x2(v[ks * 4 + 0], v[ks * 4 + 1]);
-                a[ks][2 + half] = pack_bf16x2(v[ks * 4 + 2], v[ks * 4 + 3]);
+                a[ks][half] = kval[ks][0] ? px[woff[ks][0]] : 0u;      // k = 2t, 2t+1
+                a[ks][2 + half] = kval[ks][1] ? px[woff[ks][1]] : 0u;  // k = 2t+8, 2t+9
             }
         }
         float acc[NT][4];
@@ -510,7 +541,7 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
         // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int wo = wo0 + g + half * 8;
+            const int wo = w0 + wl0 + g + half * 8;
             if (wo >= Wo) continue;
             __nv_bfloat16* dst = yrow + (long long)wo * y_cstride + 2 * t;
 #pragma unroll
@@ -532,12 +563,16 @@ static int launch_stem(const float* x, int n, int ci, int h, int w, const __nv_b
                        cudaStream_t s) {
     dim3 grid((unsigned)ceil_div(Wo, kStemRowPixels), (unsigned)ceil_div(Ho, kStemWarps), (unsigned)n);
     dim3 block(32 * kStemWarps, 1, 1);
-    if (9 * ci <= 32)
-        YL_CUDA(launch_kernel(stem_conv_kernel<CO, 2>, grid, block, 0, s, x, n, ci, h, w, wp, ci_pad, bias, yp, cs, coff,
-                              Ho, Wo, act));
-    else
-        YL_CUDA(launch_kernel(stem_conv_kernel<CO, 3>, grid, block, 0, s, x, n, ci, h, w, wp, ci_pad, bias, yp, cs, coff,
-                              Ho, Wo, act));
+#define YL_STEM(CI_)                                                                                              \
+    YL_CUDA(launch_kernel(stem_conv_kernel<CO, CI_>, grid, block, 0, s, x, n, h, w, wp, ci_pad, bias, yp, cs, coff, Ho, \
+                          Wo, act))
+    switch (ci) {
+        case 1: YL_STEM(1); break;
+        case 2: YL_STEM(2); break;
+        case 3: YL_STEM(3); break;
+        default: YL_STEM(4); break;
+    }
+#undef YL_STEM
     YL_LAUNCH_OK("stem_conv_kernel");
     return YL_OK;
 }

@@ -74,6 +74,13 @@ struct ConvTcParams {
     const __nv_bfloat16* res;
     long long res_cstride;
     int res_coff, res_c;
+    // fused Detect decode (flat 1x1 head convs): see yl_det_epilogue
+    int store_y;                 // 0: no NHWC destination (decode only)
+    int det_mode;                // yl_det_mode
+    float* det_pred;
+    int det_nc, det_A, det_anchor0, det_hw, det_w;
+    float det_stride;
+    long long det_M;             // valid pixels (rows beyond it belong to the ragged last tile)
 };
 
 constexpr int kConvTcThreads = 320;
@@ -88,6 +95,58 @@ __device__ __forceinline__ void tmem_ld_cw<16>(uint32_t taddr, uint32_t (&r)[16]
 template <>
 __device__ __forceinline__ void tmem_ld_cw<32>(uint32_t taddr, uint32_t (&r)[32]) {
     tmem_ld32(taddr, r);
+}
+
+// Fused Detect decode of one accumulator chunk (CW columns, bias already added) of pixel `m` (flat index over
+// (image, h, w)): box mode turns each 16-bin group into its DFL expectation and, once the four sides are
+// known, writes (cx, cy, w, h) * stride; class mode writes sigmoid(logit).  Consecutive lanes hold consecutive
+// pixels = consecutive anchors, so every channel row of the (B, 4+nc, A) prediction gets 128-byte coalesced
+// stores (head.py:95-126, block.py:51-69, tal.py:326-350).
+template <int CW>
+__device__ __forceinline__ void det_decode_chunk(const ConvTcParams& p, const float (&v)[CW], int c, long long m,
+                                                 float (&dist)[4]) {
+    if (m >= p.det_M) return;
+    const int b = (int)(m / p.det_hw);
+    const int al = (int)(m - (long long)b * p.det_hw);
+    float* out = p.det_pred + (long long)b * (4 + p.det_nc) * p.det_A + p.det_anchor0 + al;
+    if (p.det_mode == YL_DET_BOX) {
+        if (CW == 32) {  // reg_max == 16: two sides per chunk
+            float d2[2];
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                float mx = v[sd * 16];
+#pragma unroll
+                for (int k = 1; k < 16; ++k) mx = fmaxf(mx, v[sd * 16 + k]);
+                float ssum = 0.f, e = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float w = __expf(v[sd * 16 + k] - mx);
+                    ssum += w;
+                    e = fmaf(w, (float)k, e);
+                }
+                d2[sd] = __fdividef(e, ssum);
+            }
+            if (c == 0) {
+                dist[0] = d2[0];
+                dist[1] = d2[1];
+            } else {
+                dist[2] = d2[0];
+                dist[3] = d2[1];
+                const float ax = (float)(al % p.det_w) + 0.5f, ay = (float)(al / p.det_w) + 0.5f;
+                const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
+                out[0] = (x1 + x2) * 0.5f * p.det_stride;
+                out[(long long)p.det_A] = (y1 + y2) * 0.5f * p.det_stride;
+                out[2ll * p.det_A] = (x2 - x1) * p.det_stride;
+                out[3ll * p.det_A] = (y2 - y1) * p.det_stride;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+            const int ch = c * CW + i;
+            if (ch < p.det_nc) out[(long long)(4 + ch) * p.det_A] = __fdividef(1.f, 1.f + __expf(-v[i]));
+        }
+    }
 }
 
 // One epilogue group (4 warps, thread = accumulator row) draining the tiles of its accumulator stage.
@@ -113,6 +172,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
     uint32_t kstore = 0;                       // running store-chunk counter (selects the staging tile)
     int pend = 0, pc0 = 0, pw0 = 0, ph0 = 0, pi0 = 0;  // filled tile whose TMA store is not issued yet
     uint32_t pbuf = 0;
+    float det_dist[4] = {0.f, 0.f, 0.f, 0.f};  // decode mode: DFL distances (l, t, r, b) of this thread's pixel
 
     int lt = g;
     for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, lt += 2) {
@@ -181,6 +241,8 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                         v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
                     }
                 }
+                if (p.det_mode) det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
+                if (!p.store_y) continue;
                 if (u == 0) {
                     // the staging tile about to be overwritten must have been drained by its last TMA store:
                     // every committed store has (two tiles: the newest committed one used this tile, the one
@@ -221,6 +283,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                     }
                 }
             }
+            if (!p.store_y) continue;
             fence_proxy_async_smem();
             if (dbl) {
                 pend = 1;
@@ -295,7 +358,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA[0]);
         tma_prefetch_desc(&p.tmB);
-        tma_prefetch_desc(&p.tmY[p.y_map_first]);
+        if (p.store_y) tma_prefetch_desc(&p.tmY[p.y_map_first]);
     }
     for (int i = threadIdx.x; i < nbias; i += blockDim.x) sbias[i] = i < p.n_bias ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
@@ -570,6 +633,21 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
     if (((uintptr_t)x.data | (uintptr_t)y.data | (uintptr_t)a->w | (uintptr_t)a->bias | (uintptr_t)a->res.data |
          (uintptr_t)a->y_up.data) & 15)
         NOPE("pointers must be 16-byte aligned");
+    if (a->det.pred) {
+        const yl_det_epilogue& d = a->det;
+        if (a->k != 1 || a->stride != 1 || a->upsample2x || a->y_up.data || a->res.data || a->act)
+            NOPE("Detect-decode epilogue needs a plain 1x1 stride-1 conv without activation / residual / upsample");
+        if (d.mode == YL_DET_BOX) {
+            if (d.reg_max != 16 || y.c != 64) NOPE("Detect box decode is built for reg_max == 16 (64 channels)");
+        } else if (d.mode == YL_DET_CLS) {
+            if (y.c != d.nc || y.c > 256) NOPE("Detect class decode needs co == nc <= 256");
+        } else {
+            NOPE("bad Detect-decode mode");
+        }
+        if (d.nc < 1 || d.A < 1 || d.anchor0 < 0 || d.anchor0 + x.h * x.w > d.A) NOPE("bad Detect-decode anchor range");
+    } else if (!y.data) {
+        NOPE("null output");
+    }
     return true;
 #undef NOPE
 }
@@ -805,7 +883,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
              g_max_dyn_smem);
 
     // destination tensor maps: box = one store chunk of one tile
-    {
+    if (y.data) {
         const CUtensorMapSwizzle osw = swizzle_for_bytes(p.stg_row_bytes);
         uint32_t obox[4] = {(uint32_t)(p.stg_sub * p.cw), (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
         if (a->upsample2x) {
@@ -823,6 +901,18 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
         }
     }
 
+    p.store_y = y.data != nullptr;
+    if (a->det.pred) {
+        p.det_mode = a->det.mode;
+        p.det_pred = a->det.pred;
+        p.det_nc = a->det.nc;
+        p.det_A = a->det.A;
+        p.det_anchor0 = a->det.anchor0;
+        p.det_hw = x.h * x.w;
+        p.det_w = x.w;
+        p.det_stride = a->det.stride;
+        p.det_M = (long long)x.n * x.h * x.w;
+    }
     p.bias = a->bias;
     p.n_bias = a->co_pad;
     p.act = a->act;

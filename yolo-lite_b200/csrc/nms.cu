@@ -505,31 +505,18 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
                 csrc[pos] = s0 + ci;
             }
             __syncthreads();
-            // 3. pairwise bitmask among survivors: only the words on or right of the diagonal exist.  Row block
-            //    rbk (rows 32*rbk ..) has W - rbk words per row; the work items are flattened over them.
+            // 3. pairwise bitmask among survivors: only the words on or right of the diagonal exist.  A warp owns
+            //    rows warp, warp+32, ... (every 32-row block gives each warp one row, so the triangle is balanced);
+            //    its lanes take the 32 columns of one word: box j is read conflict-free, box i is a broadcast.
             const int W = (L + 31) >> 5;
-            {
-                int total = 0;
-                for (int rbk = 0; rbk < W; ++rbk) total += min(32, L - 32 * rbk) * (W - rbk);
-                for (int e = tid; e < total; e += kSelThreads) {
-                    int rem_e = e, rbk = 0;
-                    for (;; ++rbk) {
-                        const int c = min(32, L - 32 * rbk) * (W - rbk);
-                        if (rem_e < c) break;
-                        rem_e -= c;
-                    }
-                    const int per_row = W - rbk;
-                    const int i = rbk * 32 + rem_e / per_row;
-                    const int wd = rbk + rem_e % per_row;
-                    const float4 bi = cbox[i];
-                    const float ai = carea[i];
-                    const int j0 = wd << 5;
-                    uint32_t bits = 0;
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int j = j0 + jj;
-                        if (j > i && j < L && iou_suppresses(bi, ai, cbox[j], carea[j], thr)) bits |= 1u << jj;
-                    }
-                    mask[i * kMaskWords + wd] = bits;
+            for (int i = warp; i < L; i += kSelThreads / 32) {
+                const float4 bi = cbox[i];
+                const float ai = carea[i];
+                for (int wd = i >> 5; wd < W; ++wd) {
+                    const int j = (wd << 5) + lane;
+                    const bool sup = (j > i) && (j < L) && iou_suppresses(bi, ai, cbox[j], carea[j], thr);
+                    const uint32_t bits = __ballot_sync(0xffffffffu, sup);
+                    if (lane == 0) mask[i * kMaskWords + wd] = bits;
                 }
             }
             __syncthreads();

@@ -40,6 +40,23 @@ class Tensor(C.Structure):
     ]
 
 
+class DetEpilogue(C.Structure):
+    """Mirror of `yl_det_epilogue`."""
+
+    _fields_ = [
+        ("pred", C.c_void_p),
+        ("mode", C.c_int32),
+        ("reg_max", C.c_int32),
+        ("nc", C.c_int32),
+        ("A", C.c_int32),
+        ("anchor0", C.c_int32),
+        ("stride", C.c_float),
+    ]
+
+
+DET_NONE, DET_BOX, DET_CLS = 0, 1, 2
+
+
 class ConvArgs(C.Structure):
     _fields_ = [
         ("x", Tensor),
@@ -56,6 +73,7 @@ class ConvArgs(C.Structure):
         ("upsample2x", C.c_int32),
         ("impl", C.c_int32),
         ("_pad", C.c_int32),
+        ("det", DetEpilogue),
     ]
 
 

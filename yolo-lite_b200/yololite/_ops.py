@@ -105,10 +105,38 @@ def pack_conv(weight: torch.Tensor, bn=None, conv_bias=None, device=None) -> Pac
     return PackedConv(wp, bias, k, cig, co, ci_pad, co_pad, depthwise)
 
 
-def conv_args(x: View, y: View, pc: PackedConv, stride=1, act=True, res: View | None = None, upsample=False,
-              impl=_C.IMPL_AUTO, y_up: View | None = None) -> _C.ConvArgs:
+@dataclass
+class DetEpilogue:
+    """Fused Detect decode of a head conv (see yl_det_epilogue): `pred` is the (B, 4+nc, A) fp32 prediction."""
+
+    pred: torch.Tensor
+    mode: int            # _C.DET_BOX | _C.DET_CLS
+    reg_max: int
+    nc: int
+    anchor0: int
+    stride: float
+
+
+class NoOutput:
+    """Shape-only destination for a conv whose result is consumed by a fused epilogue (no NHWC store)."""
+
+    def __init__(self, n, h, w, c, dtype=torch.float32):
+        self.n, self.h, self.w, self.c, self.dtype = n, h, w, c, dtype
+
+    def ct(self) -> _C.Tensor:
+        return _C.Tensor(None, self.n, self.h, self.w, self.c, self.c, 0,
+                         _C.YL_F32 if self.dtype is torch.float32 else _C.YL_BF16, 0)
+
+
+def conv_args(x: View, y, pc: PackedConv, stride=1, act=True, res: View | None = None, upsample=False,
+              impl=_C.IMPL_AUTO, y_up: View | None = None, det: DetEpilogue | None = None) -> _C.ConvArgs:
     a = _C.ConvArgs()
     a.x, a.y = x.ct(), y.ct()
+    if det is not None:
+        assert det.pred.is_cuda and det.pred.dtype == torch.float32 and det.pred.is_contiguous() and det.pred.dim() == 3
+        a.det.pred = det.pred.data_ptr()
+        a.det.mode, a.det.reg_max, a.det.nc = det.mode, det.reg_max, det.nc
+        a.det.A, a.det.anchor0, a.det.stride = det.pred.shape[2], det.anchor0, float(det.stride)
     a.res = res.ct() if res is not None else _C.null_tensor()
     a.y_up = y_up.ct() if y_up is not None else _C.null_tensor()
     a.w, a.bias = pc.w.data_ptr(), pc.bias.data_ptr()
@@ -119,8 +147,8 @@ def conv_args(x: View, y: View, pc: PackedConv, stride=1, act=True, res: View | 
     return a
 
 
-def conv(x: View, y: View, pc: PackedConv, stride=1, act=True, res=None, upsample=False, impl=_C.IMPL_AUTO,
-         y_up=None):
+def conv(x: View, y, pc: PackedConv, stride=1, act=True, res=None, upsample=False, impl=_C.IMPL_AUTO,
+         y_up=None, det=None):
     lib = _C.load()
     if pc.depthwise:
         assert stride == 1 and pc.k == 3 and not upsample, "depthwise path is 3x3 stride 1"
@@ -128,7 +156,7 @@ def conv(x: View, y: View, pc: PackedConv, stride=1, act=True, res=None, upsampl
         _C.check(lib.yl_dwconv3x3(C.byref(x.ct()), C.byref(y.ct()), pc.w.data_ptr(), pc.bias.data_ptr(), int(act),
                                   addp, _C.stream_ptr()), "yl_dwconv3x3")
         return
-    a = conv_args(x, y, pc, stride, act, res, upsample, impl, y_up)
+    a = conv_args(x, y, pc, stride, act, res, upsample, impl, y_up, det)
     _C.check(lib.yl_conv_bn_act(C.byref(a), _C.stream_ptr()), "yl_conv_bn_act")
 
 

@@ -58,6 +58,7 @@ class Builder:
         self.bytes = 0
         self.meta: list[dict] = []
         self.ingest: NchwInput | None = None
+        self.want_raw = True               # Detect: also write the raw head maps (module-level API)
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -99,7 +100,9 @@ class Builder:
         return x.view
 
     def conv(self, x: View, pc: PackedConv, stride=1, act=True, out=None, res: View | None = None,
-             upsample=False, out_dtype=torch.bfloat16, impl=_C.IMPL_AUTO) -> View:
+             upsample=False, out_dtype=torch.bfloat16, impl=_C.IMPL_AUTO, det=None, store=True) -> View:
+        """`det`: _ops.DetEpilogue fusing the Detect decode into this conv; with `store=False` the conv result is
+        consumed by that epilogue only and no NHWC tensor is written (returns None)."""
         k = pc.k
         dual = None
         if isinstance(out, DualDest):
@@ -121,7 +124,11 @@ class Builder:
         ho = (x.h + 2 * (k // 2) - k) // stride + 1
         wo = (x.w + 2 * (k // 2) - k) // stride + 1
         u = 2 if upsample else 1
-        y = self._out(out, x.n, ho * u, wo * u, pc.co, out_dtype)
+        if not store:
+            assert det is not None and out is None and not pc.depthwise
+            y = _ops.NoOutput(x.n, ho, wo, pc.co, out_dtype)
+        else:
+            y = self._out(out, x.n, ho * u, wo * u, pc.co, out_dtype)
         if pc.depthwise:
             assert stride == 1 and k == 3 and not upsample
             xt, yt = x.ct(), y.ct()
@@ -134,17 +141,23 @@ class Builder:
         y_up = None
         if dual is not None:
             y_up = dual.up_view = self._out(dual.up, x.n, 2 * ho, 2 * wo, pc.co, out_dtype)
-        a = _ops.conv_args(x, y, pc, stride, act, res, upsample, impl, y_up)
+        a = _ops.conv_args(x, y, pc, stride, act, res, upsample, impl, y_up, det)
         opx = x.n * ho * wo
         esz = 4 if out_dtype is torch.float32 else 2
         tc = impl != _C.IMPL_DIRECT and bool(self.lib.yl_conv_tc_supported(C.byref(a)))
-        self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc), kind="conv_tc" if tc else "conv_direct",
-                   bytes_=x.n * x.h * x.w * x.c * 2 + opx * pc.co * esz * u * u + k * k * x.c * pc.co * 2
+        if det is not None and not tc:
+            raise RuntimeError(f"fused Detect decode rejected by the tcgen05 path: {x.c}->{pc.co} k{k}")
+        out_bytes = opx * pc.co * esz * u * u if store else 0
+        if det is not None:   # decoded rows of the prediction: 4 box values or nc scores per anchor, fp32
+            out_bytes += opx * (4 if det.mode == _C.DET_BOX else det.nc) * 4
+        self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc, det), kind="conv_tc" if tc else "conv_direct",
+                   bytes_=x.n * x.h * x.w * x.c * 2 + out_bytes + k * k * x.c * pc.co * 2
                    + (opx * pc.co * 2 if res is not None else 0) + (4 * opx * pc.co * esz if y_up is not None else 0),
                    flops=2 * opx * pc.co * x.c * k * k,
                    desc=f"{x.c}->{pc.co} k{k}s{stride} {x.h}x{x.w}" + (" +res" if res is not None else "")
-                   + (" up2" if upsample else "") + (" +up2" if y_up is not None else "") + (" f32" if esz == 4 else ""))
-        return y
+                   + (" up2" if upsample else "") + (" +up2" if y_up is not None else "")
+                   + (" f32" if esz == 4 and store else "") + (" +decode" if det is not None else ""))
+        return y if store else None
 
     def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):
         ts = [v.ct() for v in (x, y1, y2, y3)]

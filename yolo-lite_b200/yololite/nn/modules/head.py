@@ -32,6 +32,8 @@ class Detect(YLModule):
     anchors = torch.empty(0)
     strides = torch.empty(0)
     legacy = False
+    #: decode (DFL / anchors / sigmoid) inside the epilogue of the last head convs instead of a separate kernel
+    fuse_decode = True
 
     def __init__(self, nc=80, ch=()):
         super().__init__()
@@ -68,13 +70,39 @@ class Detect(YLModule):
         if float(self.stride.sum()) == 0.0:
             raise RuntimeError("Detect.stride is unset (it is filled in by DetectionModel)")
         nbox = 4 * self.reg_max
+        want_raw = getattr(g, "want_raw", True)
+        fuse = self.fuse_decode and self.reg_max == 16 and self.nc <= 256 and self.nc % 8 == 0
         raws = []
+        if not fuse:
+            for i, x in enumerate(feats):
+                raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32)
+                emit_any(g, self.cv2[i], x, out=raw.slice(0, nbox), out_dtype=torch.float32)
+                emit_any(g, self.cv3[i], x, out=raw.slice(nbox, self.nc), out_dtype=torch.float32)
+                raws.append(raw)
+            y = g.detect_decode(raws, [float(s) for s in self.stride], self.reg_max, self.nc)
+            return y, raws
+        # fused: the last 1x1 conv of each branch decodes its logits straight into the prediction (DFL + anchors
+        # + stride / sigmoid in the conv epilogue); the raw (B, H, W, no) maps are written only on request
+        from ... import _C, _ops
+        from ._emit import packed
+
+        feats = [g.mat(x) for x in feats]
+        n = feats[0].n
+        A = sum(x.h * x.w for x in feats)
+        y = torch.empty((n, 4 + self.nc, A), dtype=torch.float32, device=g.device)
+        g.buffers.append(y)
+        a0 = 0
         for i, x in enumerate(feats):
-            raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32)
-            emit_any(g, self.cv2[i], x, out=raw.slice(0, nbox), out_dtype=torch.float32)
-            emit_any(g, self.cv3[i], x, out=raw.slice(nbox, self.nc), out_dtype=torch.float32)
-            raws.append(raw)
-        y = g.detect_decode(raws, [float(s) for s in self.stride], self.reg_max, self.nc)
+            raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32) if want_raw else None
+            for branch, mode, lo, cnt in ((self.cv2[i], _C.DET_BOX, 0, nbox), (self.cv3[i], _C.DET_CLS, nbox, self.nc)):
+                t = emit_any(g, branch[:-1], x)
+                last = branch[-1]
+                det = _ops.DetEpilogue(y, mode, self.reg_max, self.nc, a0, float(self.stride[i]))
+                g.conv(t, packed(last, None, last), 1, act=False, out=raw.slice(lo, cnt) if want_raw else None,
+                       out_dtype=torch.float32, det=det, store=want_raw)
+            if want_raw:
+                raws.append(raw)
+            a0 += x.h * x.w
         return y, raws
 
     def _yl_export(self, g, res):

@@ -150,7 +150,7 @@ class BaseModel(YLModule):
     def predict(self, x, profile=False, visualize=False, augment=False, embed=None):
         if augment or visualize or embed or profile:
             raise NotImplementedError("augment / visualize / embed / profile are not part of the inference hot path")
-        out = self.infer(x)
+        out = self.infer(x, want_raw=True)   # the module-level API returns the raw head maps like the reference
         if self.clone_outputs:
             y, raws = out
             return y.clone(), [r.clone() for r in raws]
@@ -283,13 +283,14 @@ class BaseModel(YLModule):
         memo[k] = c
         return c
 
-    def _get_plan(self, shape, dev):
+    def _get_plan(self, shape, dev, want_raw=False):
         plans = self.__dict__.setdefault("_yl_plans", {})
-        key = (tuple(shape), dev.index, bool(self.use_cuda_graph))
+        key = (tuple(shape), dev.index, bool(self.use_cuda_graph), bool(want_raw))
         entry = plans.get(key)
         if entry is None:
             with torch.cuda.device(dev):
                 g = _plan.Builder(dev)
+                g.want_raw = bool(want_raw)   # Detect writes its raw (B, H, W, no) maps only on request
                 static_in = torch.zeros(tuple(shape), dtype=torch.float32, device=dev)
                 xin = g.input_nchw(static_in)
                 y, raws = self._emit(g, xin)
@@ -302,11 +303,12 @@ class BaseModel(YLModule):
         return entry
 
     @torch.no_grad()
-    def infer(self, x: torch.Tensor):
+    def infer(self, x: torch.Tensor, want_raw: bool = False):
         """Engine entry: NCHW float image batch on CUDA -> (y (B, 4+nc, A) fp32, [raw (B, no, H, W) views]).
 
-        The returned tensors alias the plan's static buffers and are overwritten by the next call with the same
-        shape."""
+        The raw head maps are only needed by callers of the module-level API (`forward`); the engine path
+        (`want_raw=False`) gets an empty list and the plan never writes them.  The returned tensors alias the
+        plan's static buffers and are overwritten by the next call with the same shape."""
         if not isinstance(x, torch.Tensor) or x.dim() != 4:
             raise TypeError("expected a (B, C, H, W) tensor")
         if not x.is_cuda:
@@ -319,7 +321,7 @@ class BaseModel(YLModule):
         s = int(self.stride.max()) if hasattr(self, "stride") else 32
         if x.shape[2] % s or x.shape[3] % s:
             raise ValueError(f"image size {tuple(x.shape[2:])} must be a multiple of the model stride {s}")
-        plan, static_in, y, raws = self._get_plan(x.shape, dev)
+        plan, static_in, y, raws = self._get_plan(x.shape, dev, want_raw)
         with torch.cuda.device(dev):
             if x.dtype == torch.float32 and x.is_contiguous():
                 plan.run(ingest_ptr=x.data_ptr())          # zero-copy: the ingest kernel reads x directly
