@@ -126,16 +126,30 @@ def cpu_reference_step(sd, x):
     return nms_ref.non_max_suppression(y.numpy(), conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
 
 
-def time_cpu(model_sd, batch, reps, warm=1):
+def time_cpu(model_sd, batch, reps, warm=1, budget_s=None):
+    """Median images/s of the CPU path on `batch`-image steps; with `budget_s` keep repeating (>= reps) until about
+    that much CPU wall time has been spent, so the baseline is a 10-30 s sample, not a single cold step."""
     x = synth_images(batch, 1, seed=0)[0]
     for _ in range(warm):
         cpu_reference_step(model_sd, x)
     ts = []
-    for _ in range(reps):
+    t_start = time.perf_counter()
+    while len(ts) < reps or (budget_s is not None and time.perf_counter() - t_start < budget_s and len(ts) < 400):
         t0 = time.perf_counter()
         cpu_reference_step(model_sd, x)
         ts.append(time.perf_counter() - t0)
     return batch / statistics.median(ts), ts
+
+
+def ncu_traffic(kernel, model_name, batch):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu` capture of this workload (profiles/traffic.json, written by tools/ncu_traffic.py), or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text())
+    e = d.get(f"{model_name}_bs{batch}", {}).get(kernel)
+    return None if e is None else round(e["dram_bytes_per_launch"], 1)
 
 
 def peaks():
@@ -287,7 +301,9 @@ def main():
         tk = kinds[top]
         ach = tk["bytes"] / 1e9 / (tk["ms"] / 1e3)
         roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(ach / hbm, 4), "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({src})",
+                "frac": round(ach / hbm, 4), "traffic": ncu_traffic(top, model_name, a.batch),
+                "algorithmic_bytes_per_launch": round(tk["bytes"] / tk["launches"], 1),
+                "peak_source": f"MEASURED_PEAKS.json ({src})",
                 "launches_per_step": tk["launches"], "avg_launch_us": round(tk["ms"] * 1e3 / tk["launches"], 2),
                 "tensor_tflops": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3), 1), "tensor_peak_tflops": tf,
                 "tensor_frac": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3) / tf, 4)}
@@ -303,10 +319,10 @@ def main():
     if rank == 0 and not a.no_cpu_baseline:
         threads = max(1, min(os.cpu_count() or 1, 64))
         torch.set_num_threads(threads)
-        v, ts = time_cpu(sd_cpu, 8, reps=3, warm=1)
+        v, ts = time_cpu(sd_cpu, 8, reps=3, warm=1, budget_s=12.0)
         cpu_b = {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": "port",
-                 "sample": f"oracle port (yolo11_ref fp32 unfused + nms_ref), 8 of {a.batch} images x3 reps, "
-                           f"{sum(ts):.1f}s CPU wall"}
+                 "sample": f"oracle port (yolo11_ref fp32 unfused + nms_ref), 8-image steps of the bs={a.batch} "
+                           f"workload x{len(ts)} reps, {sum(ts):.1f}s CPU wall, median step"}
 
     if rank == 0:
         total_images = a.batch * world * a.steps

@@ -309,7 +309,9 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
             bulk_commit();
         }
     }
-    if (leader) bulk_wait<0>();
+    // the staging tiles must outlive the TMA engine's reads of them; the global writes themselves are flushed by
+    // the grid's completion (which is what the next kernel's griddepcontrol.wait / stream order waits for)
+    if (leader) bulk_wait_read<0>();
 }
 
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
