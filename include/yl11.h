@@ -55,6 +55,11 @@ const char* yl_last_error_string(void);
 /* Bind to `device`, check it is sm_100, resolve the TMA encoder and opt kernels into large shared memory.
  * Must be called once per process before any other entry point. */
 int yl_init(int device);
+/* Programmatic dependent launch: by default every kernel of the library is launched with the programmatic
+ * stream-serialization attribute (its prologue may overlap the previous kernel of the stream; it executes
+ * griddepcontrol.wait before touching activations).  yl_set_pdl(0) makes subsequent launches plain (used for a
+ * launch that follows a cross-stream event wait); returns the previous setting.  Process-wide, not thread-safe. */
+int yl_set_pdl(int enabled);
 
 /* ---- weight preparation (one-time) ----------------------------------------------------------------------
  * Replaces the fold the reference never performs at inference (utils/torch_utils.py:182-209 is the formula:

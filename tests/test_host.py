@@ -123,3 +123,23 @@ def test_product_never_imports_oracle():
         assert "import oracle" not in src and "from oracle" not in src, f
     for f in pkg.rglob("*.cu"):
         assert "oracle/" not in f.read_text().replace("oracle/ ", "")
+
+
+def test_plan_dependency_tracking_on_channel_slices():
+    """Builder._track derives RAW / WAR / WAW edges from channel-slice accesses: writers of disjoint concat
+    slices are independent, a reader depends on every overlapping writer, an overwrite waits for its readers."""
+    import torch
+
+    from yololite._ops import View
+    from yololite._plan import Builder
+
+    b = Builder.__new__(Builder)
+    b._access = {}
+    buf = torch.zeros(1, 2, 2, 64)
+    other = torch.zeros(1, 2, 2, 16)
+    assert b._track(0, (), (View(buf, 0, 32),)) == ()                  # producer of slice [0, 32)
+    assert b._track(1, (), (View(buf, 32, 32),)) == ()                 # producer of slice [32, 64): independent
+    assert b._track(2, (View(buf, 16, 32),), (View(other, 0, 16),)) == (0, 1)   # reads across both slices
+    assert b._track(3, (View(buf, 0, 16),), ()) == (0,)                # reads only the first producer's slice
+    assert b._track(4, (View(other, 0, 16),), (View(buf, 0, 64),)) == (0, 1, 2, 3)  # overwrite: WAW + WAR
+    assert b._track(5, (View(buf, 40, 8),), ()) == (1, 4)              # every overlapping earlier writer

@@ -26,13 +26,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 EncodeTiledFn get_encode_tiled() { return g_encode; }
 
+static int g_pdl_env = -1;   // YL_PDL environment switch (default on)
+static int g_pdl_user = 1;   // yl_set_pdl()
+
 bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) {
+    if (g_pdl_env < 0) {
         const char* e = getenv("YL_PDL");
-        v = (e && *e) ? (atoi(e) != 0) : 1;
+        g_pdl_env = (e && *e) ? (atoi(e) != 0) : 1;
     }
-    return v != 0;
+    return g_pdl_env != 0 && g_pdl_user != 0;
 }
 
 int init_conv_tc();    // conv_tc.cu
@@ -45,6 +47,12 @@ int init_pool();       // pool.cu
 extern "C" {
 
 int yl_version(void) { return YL11_VERSION; }
+
+int yl_set_pdl(int enabled) {
+    const int prev = yl::g_pdl_user;
+    yl::g_pdl_user = enabled ? 1 : 0;
+    return prev;
+}
 
 const char* yl_last_error_string(void) { return yl::g_err; }
 

@@ -5,9 +5,15 @@ performs, with every activation buffer pre-allocated (NHWC bf16) and channel con
 aliasing (producers write straight into channel slices of the consumer's buffer).  `Plan.run()` replays the
 pre-marshalled ctypes calls on the current stream; `Plan.capture()` wraps that replay in a CUDA graph so a
 forward is one `cudaGraphLaunch` (the reference issues ~300 ATen kernels per forward, nn/tasks.py:118-145).
+
+The Builder also records which buffer slices every launch reads and writes.  Emitters may put independent
+sub-chains (the Detect branches of each pyramid level) on side "lanes" (`with g.lane(k):`); at capture time a
+lane becomes a forked stream whose launches wait only on their true producers, so the CUDA graph has parallel
+branches and the launch-latency-bound tail of small layers overlaps the big head convolutions.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Callable
 
@@ -54,6 +60,10 @@ class Builder:
         self.device = device
         self.lib = _C.init(device)
         self.calls: list[tuple] = []      # (fn, args tuple without stream, keepalive)
+        self.lanes: list[int] = []        # lane (forked stream) of every call; 0 = the main stream
+        self.deps: list[tuple] = []       # per call: indices of earlier calls whose results it reads / overwrites
+        self._cur_lane = 0
+        self._access: dict = {}           # buffer data_ptr -> [(c0, c1, call index, is_write)]
         self.buffers: list[torch.Tensor] = []
         self.bytes = 0
         self.meta: list[dict] = []
@@ -75,8 +85,38 @@ class Builder:
         assert (out.n, out.h, out.w, out.c) == (n, h, w, c), ((out.n, out.h, out.w, out.c), (n, h, w, c))
         return out
 
-    def _push(self, fn, *args, keep=(), kind="", bytes_=0, flops=0, desc=""):
+    @contextlib.contextmanager
+    def lane(self, k: int):
+        """Launches emitted inside run on side lane `k` (a forked stream at graph capture)."""
+        prev, self._cur_lane = self._cur_lane, int(k)
+        try:
+            yield
+        finally:
+            self._cur_lane = prev
+
+    def _track(self, idx, reads, writes):
+        """RAW / WAR / WAW dependencies of call `idx` from the channel-slice access history of each buffer."""
+        deps = set()
+        for views, is_write in ((reads, False), (writes, True)):
+            for v in views:
+                if v is None:
+                    continue
+                if isinstance(v, torch.Tensor):
+                    key, c0, c1 = v.data_ptr(), 0, 1 << 30
+                else:
+                    key, c0, c1 = v.buf.data_ptr(), v.coff, v.coff + v.c
+                hist = self._access.setdefault(key, [])
+                for (a0, a1, j, w) in hist:
+                    if j != idx and a0 < c1 and c0 < a1 and (w or is_write):
+                        deps.add(j)
+                hist.append((c0, c1, idx, is_write))
+        return tuple(sorted(deps))
+
+    def _push(self, fn, *args, keep=(), kind="", bytes_=0, flops=0, desc="", reads=(), writes=()):
+        idx = len(self.calls)
         self.calls.append((fn, args, keep))
+        self.lanes.append(self._cur_lane)
+        self.deps.append(self._track(idx, reads, writes))
         # algorithmic work of the launch (each operand touched once): the roofline numerators of DESIGN.md
         self.meta.append({"kind": kind or fn.__name__, "bytes": int(bytes_), "flops": int(flops), "desc": desc})
 
@@ -95,7 +135,7 @@ class Builder:
             v = self.alloc(x.n, x.h, x.w, x.c)
             t = v.ct()
             self._push(self.lib.yl_nchw_to_nhwc, x.static.data_ptr(), C.byref(t), keep=(t, x.static),
-                       kind="ingest_nchw_to_nhwc", bytes_=x.n * x.c * x.h * x.w * (4 + 2))
+                       kind="ingest_nchw_to_nhwc", bytes_=x.n * x.c * x.h * x.w * (4 + 2), writes=(v,))
             x.view = v
         return x.view
 
@@ -118,7 +158,8 @@ class Builder:
                 self._push(self.lib.yl_stem_conv, x.static.data_ptr(), x.n, x.c, x.h, x.w, pc.w.data_ptr(), pc.ci_pad,
                            pc.bias.data_ptr(), C.byref(yt), int(act), keep=(yt, pc, x.static), kind="stem_conv",
                            bytes_=x.n * x.c * x.h * x.w * 4 + x.n * ho * wo * pc.co * 2,
-                           flops=2 * x.n * ho * wo * pc.co * x.c * 9, desc=f"{x.c}->{pc.co} k3s2 {x.h}x{x.w} nchw-f32 in")
+                           flops=2 * x.n * ho * wo * pc.co * x.c * 9, desc=f"{x.c}->{pc.co} k3s2 {x.h}x{x.w} nchw-f32 in",
+                           writes=(y,))
                 return y
             x = self.mat(x)
         ho = (x.h + 2 * (k // 2) - k) // stride + 1
@@ -136,7 +177,8 @@ class Builder:
             px = x.n * x.h * x.w
             self._push(self.lib.yl_dwconv3x3, C.byref(xt), C.byref(yt), pc.w.data_ptr(), pc.bias.data_ptr(), int(act),
                        C.byref(rt) if rt is not None else None, keep=(xt, yt, rt, pc), kind="dwconv3x3",
-                       bytes_=px * x.c * 2 * (2 + (res is not None)) + 9 * x.c * 2, flops=2 * 9 * px * x.c)
+                       bytes_=px * x.c * 2 * (2 + (res is not None)) + 9 * x.c * 2, flops=2 * 9 * px * x.c,
+                       reads=(x, res), writes=(y,))
             return y
         y_up = None
         if dual is not None:
@@ -156,20 +198,21 @@ class Builder:
                    flops=2 * opx * pc.co * x.c * k * k,
                    desc=f"{x.c}->{pc.co} k{k}s{stride} {x.h}x{x.w}" + (" +res" if res is not None else "")
                    + (" up2" if upsample else "") + (" +up2" if y_up is not None else "")
-                   + (" f32" if esz == 4 and store else "") + (" +decode" if det is not None else ""))
+                   + (" f32" if esz == 4 and store else "") + (" +decode" if det is not None else ""),
+                   reads=(x, res), writes=(y if store else None, y_up))
         return y if store else None
 
     def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):
         ts = [v.ct() for v in (x, y1, y2, y3)]
         self._push(self.lib.yl_sppf_pool, *[C.byref(t) for t in ts], k, keep=tuple(ts), kind="sppf_pool",
-                   bytes_=x.n * x.h * x.w * x.c * 2 * 4)
+                   bytes_=x.n * x.h * x.w * x.c * 2 * 4, reads=(x,), writes=(y1, y2, y3))
 
     def upsample2x(self, x: View, out=None) -> View:
         x = self.mat(x)
         y = self._out(out, x.n, 2 * x.h, 2 * x.w, x.c)
         xt, yt = x.ct(), y.ct()
         self._push(self.lib.yl_upsample2x, C.byref(xt), C.byref(yt), keep=(xt, yt), kind="upsample2x",
-                   bytes_=x.n * x.h * x.w * x.c * 2 * 5)
+                   bytes_=x.n * x.h * x.w * x.c * 2 * 5, reads=(x,), writes=(y,))
         return y
 
     def copy(self, x: View, out=None) -> View:
@@ -177,7 +220,7 @@ class Builder:
         y = self._out(out, x.n, x.h, x.w, x.c)
         xt, yt = x.ct(), y.ct()
         self._push(self.lib.yl_copy_slice, C.byref(xt), C.byref(yt), keep=(xt, yt), kind="copy_slice",
-                   bytes_=x.n * x.h * x.w * x.c * 2 * 2)
+                   bytes_=x.n * x.h * x.w * x.c * 2 * 2, reads=(x,), writes=(y,))
         return y
 
     def attention(self, qkv: View, heads: int, key_dim: int, head_dim: int, scale: float, out=None) -> View:
@@ -186,7 +229,7 @@ class Builder:
         ntok = qkv.h * qkv.w
         self._push(self.lib.yl_psa_attention, C.byref(qt), C.byref(yt), heads, key_dim, head_dim, float(scale),
                    keep=(qt, yt), kind="psa_attention", bytes_=qkv.n * ntok * (qkv.c + heads * head_dim) * 2,
-                   flops=2 * qkv.n * heads * ntok * ntok * (key_dim + head_dim))
+                   flops=2 * qkv.n * heads * ntok * ntok * (key_dim + head_dim), reads=(qkv,), writes=(y,))
         return y
 
     def detect_decode(self, levels: list[View], strides, reg_max: int, nc: int) -> torch.Tensor:
@@ -197,7 +240,8 @@ class Builder:
         arr = (_C.Tensor * len(levels))(*[v.ct() for v in levels])
         st = (C.c_float * len(levels))(*[float(s) for s in strides])
         self._push(self.lib.yl_detect_decode, arr, len(levels), st, reg_max, nc, y.data_ptr(), keep=(arr, st),
-                   kind="detect_decode", bytes_=n * a * ((4 * reg_max + nc) * 4 + (4 + nc) * 4))
+                   kind="detect_decode", bytes_=n * a * ((4 * reg_max + nc) * 4 + (4 + nc) * 4), reads=tuple(levels),
+                   writes=(y,))
         return y
 
     def to_nchw(self, x: View) -> torch.Tensor:
@@ -206,7 +250,7 @@ class Builder:
         self.buffers.append(out)
         xt = x.ct()
         self._push(self.lib.yl_nhwc_to_nchw, C.byref(xt), out.data_ptr(), keep=(xt,), kind="export_nhwc_to_nchw",
-                   bytes_=x.n * x.h * x.w * x.c * (x.buf.element_size() + 4))
+                   bytes_=x.n * x.h * x.w * x.c * (x.buf.element_size() + 4), reads=(x,), writes=(out,))
         return out
 
     def finish(self) -> "Plan":
@@ -219,6 +263,8 @@ class Plan:
     def __init__(self, b: Builder):
         self.device = b.device
         self.calls = b.calls
+        self.lanes = b.lanes
+        self.deps = b.deps
         self.meta = b.meta
         self.buffers = b.buffers
         self.bytes = b.bytes
@@ -274,7 +320,57 @@ class Plan:
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run_eager(skip)
+            if any(self.lanes[skip:]):
+                self._run_lanes(skip)
+            else:
+                self.run_eager(skip)
         self.graph = g
         self._skip = skip
         return self
+
+    def _run_lanes(self, skip: int = 0):
+        """Issue calls[skip:] with every lane on its own stream forked from the current one: a launch waits (via
+        events) only for its cross-lane producers, same-lane order is stream order, and all lanes rejoin the
+        current stream at the end.  Under stream capture this yields a graph with parallel branches."""
+        main = torch.cuda.current_stream(self.device)
+        streams = {0: main}
+        n = len(self.calls)
+        # fork every side lane from the capturing stream before any work is issued on it
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for lane in sorted(set(self.lanes[skip:])):
+            if lane != 0:
+                st = streams[lane] = torch.cuda.Stream(device=self.device)
+                st.wait_event(fork)
+        needed = set()                    # calls whose completion some other lane waits for
+        for i in range(skip, n):
+            for d in self.deps[i]:
+                if d >= skip and self.lanes[d] != self.lanes[i]:
+                    needed.add(d)
+        events = {}
+        check = _C.check
+        lib = _C.load()
+        for i in range(skip, n):
+            fn, args, _ = self.calls[i]
+            lane = self.lanes[i]
+            st = streams[lane]
+            cross = [d for d in self.deps[i] if d >= skip and self.lanes[d] != lane]
+            for d in cross:
+                st.wait_event(events[d])
+            # a launch that follows an event wait keeps a plain (full) dependency: programmatic dependent launch
+            # is only used between consecutive kernels of one lane
+            if cross:
+                lib.yl_set_pdl(0)
+            rc = fn(*args, st.cuda_stream)
+            if cross:
+                lib.yl_set_pdl(1)
+            if rc != 0:
+                check(rc, fn.__name__)
+            if i in needed:
+                ev = events[i] = torch.cuda.Event()
+                ev.record(st)
+        for lane, st in streams.items():
+            if lane != 0:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)

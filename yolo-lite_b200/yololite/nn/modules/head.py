@@ -34,6 +34,8 @@ class Detect(YLModule):
     legacy = False
     #: decode (DFL / anchors / sigmoid) inside the epilogue of the last head convs instead of a separate kernel
     fuse_decode = True
+    #: put the per-level box / class chains on parallel graph branches
+    parallel_branches = True
 
     def __init__(self, nc=80, ch=()):
         super().__init__()
@@ -94,12 +96,17 @@ class Detect(YLModule):
         a0 = 0
         for i, x in enumerate(feats):
             raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32) if want_raw else None
-            for branch, mode, lo, cnt in ((self.cv2[i], _C.DET_BOX, 0, nbox), (self.cv3[i], _C.DET_CLS, nbox, self.nc)):
-                t = emit_any(g, branch[:-1], x)
-                last = branch[-1]
-                det = _ops.DetEpilogue(y, mode, self.reg_max, self.nc, a0, float(self.stride[i]))
-                g.conv(t, packed(last, None, last), 1, act=False, out=raw.slice(lo, cnt) if want_raw else None,
-                       out_dtype=torch.float32, det=det, store=want_raw)
+            for j, (branch, mode, lo, cnt) in enumerate(((self.cv2[i], _C.DET_BOX, 0, nbox),
+                                                          (self.cv3[i], _C.DET_CLS, nbox, self.nc))):
+                # every (level, branch) chain depends only on its pyramid feature: side lanes let the graph run
+                # them next to the rest of the neck (the last level's box branch stays on the main lane)
+                lane = 0 if (i == self.nl - 1 and j == 0) or not self.parallel_branches else 1 + 2 * i + j
+                with g.lane(lane):
+                    t = emit_any(g, branch[:-1], x)
+                    last = branch[-1]
+                    det = _ops.DetEpilogue(y, mode, self.reg_max, self.nc, a0, float(self.stride[i]))
+                    g.conv(t, packed(last, None, last), 1, act=False, out=raw.slice(lo, cnt) if want_raw else None,
+                           out_dtype=torch.float32, det=det, store=want_raw)
             if want_raw:
                 raws.append(raw)
             a0 += x.h * x.w
