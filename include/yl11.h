@@ -60,6 +60,10 @@ int yl_init(int device);
  * griddepcontrol.wait before touching activations).  yl_set_pdl(0) makes subsequent launches plain (used for a
  * launch that follows a cross-stream event wait); returns the previous setting.  Process-wide, not thread-safe. */
 int yl_set_pdl(int enabled);
+/* Debug aid: the next `capacity` tcgen05 conv launches record 8 %globaltimer stamps (ns) of CTA 0 into
+ * device_buf[launch][8]: start, prologue done, dependency wait done, first operands landed, first accumulator
+ * ready, last store issued, staging drained, exit.  NULL disables.  Not for production use. */
+int yl_debug_timeline(unsigned long long* device_buf, int capacity);
 
 /* ---- weight preparation (one-time) ----------------------------------------------------------------------
  * Replaces the fold the reference never performs at inference (utils/torch_utils.py:182-209 is the formula:

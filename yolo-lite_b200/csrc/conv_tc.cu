@@ -81,7 +81,18 @@ struct ConvTcParams {
     int det_nc, det_A, det_anchor0, det_hw, det_w;
     float det_stride;
     long long det_M;             // valid pixels (rows beyond it belong to the ragged last tile)
+    unsigned long long* dbg;     // optional timeline slot (8 x %globaltimer ns, written by CTA 0): yl_debug_timeline
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define YL_STAMP(slot)                                                   \
+    do {                                                                 \
+        if (p.dbg && blockIdx.x == 0) p.dbg[slot] = globaltimer_ns();    \
+    } while (0)
 
 constexpr int kConvTcThreads = 320;
 constexpr int kEpiGroupThreads = 128;
@@ -194,6 +205,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
         const uint32_t ph = (uint32_t)(lt >> 1) & 1u;
         mbar_wait(&tfull_bar[g], ph);
         tc_fence_after();
+        if (leader && g == 0 && lt == 0) YL_STAMP(4);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.acc_stride);
 
         for (int s = 0; s < p.nstore; ++s, ++kstore) {
@@ -213,6 +225,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                         rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
                 }
                 tmem_ld_wait();
+                if (leader && g == 0 && lt == 0 && c < 3) YL_STAMP(c == 0 ? 8 : (c == 1 ? 12 : 14));
                 if (c == p.nchunks - 1) {
                     // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
                     tc_fence_before();
@@ -243,6 +256,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                 }
                 if (p.det_mode) det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
                 if (!p.store_y) continue;
+                if (leader && g == 0 && lt == 0 && c < 2) YL_STAMP(c == 0 ? 9 : 13);
                 if (u == 0) {
                     // the staging tile about to be overwritten must have been drained by its last TMA store:
                     // every committed store has (two tiles: the newest committed one used this tile, the one
@@ -258,6 +272,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                         }
                         pend = 0;
                     }
+                    if (leader && g == 0 && lt == 0 && (c == 0 || c == 2)) YL_STAMP(c == 0 ? 10 : 15);
                 }
                 const uint32_t base_off = row_off + (uint32_t)u * sub_bytes;
                 if (p.y_f32) {
@@ -285,6 +300,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
             }
             if (!p.store_y) continue;
             fence_proxy_async_smem();
+            if (leader && g == 0 && lt == 0 && s == 0) YL_STAMP(11);
             if (dbl) {
                 pend = 1;
                 pbuf = buf;
@@ -309,9 +325,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
             bulk_commit();
         }
     }
+    if (leader && g == 0) YL_STAMP(5);
     // the staging tiles must outlive the TMA engine's reads of them; the global writes themselves are flushed by
     // the grid's completion (which is what the next kernel's griddepcontrol.wait / stream order waits for)
     if (leader) bulk_wait_read<0>();
+    if (leader && g == 0) YL_STAMP(6);
 }
 
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
@@ -341,6 +359,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
 
     // programmatic dependent launch: let the next kernel of the stream start its prologue as our CTAs retire
     griddep_launch_dependents();
+    if (threadIdx.x == 0) YL_STAMP(0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -367,9 +386,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) YL_STAMP(1);
     // everything above touched only constants (weights' bias, tensor maps); activations written by the
     // previous kernel of the stream are read / overwritten only after it has completed
     griddep_wait();
+    if (threadIdx.x == 0) YL_STAMP(2);
 
     const int taps = p.ksize * p.ksize;
     const int kiters = taps * p.cin_blocks;
@@ -472,6 +493,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
                 mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
+                if (leader && tile == (int)blockIdx.x) YL_STAMP(3);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
                 const uint32_t a0 = smem_u32(sA + (size_t)st * p.a_bytes);
                 if (leader) {
@@ -508,6 +530,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
                 for (int ki = 0; ki < kiters; ++ki) {
                     mbar_wait(&full_bar[st], ph);
                     tc_fence_after();
+                    if (leader && tile == (int)blockIdx.x && ki == 0) YL_STAMP(3);
                     if (leader) {
                         const uint64_t da = umma_desc_kmajor(smem_u32(sA + (size_t)st * p.a_bytes), rb);
                         const uint64_t db = umma_desc_kmajor(smem_u32(sB + (size_t)(p.wres ? ki : st) * p.b_bytes), rb);
@@ -544,9 +567,12 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (threadIdx.x == 0) YL_STAMP(7);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static unsigned long long* g_dbg_buf = nullptr;  // yl_debug_timeline: device buffer of [capacity][8] timestamps
+static int g_dbg_cap = 0, g_dbg_next = 0;
 static int g_max_dyn_smem = 0;
 static int g_num_sms = 148;
 
@@ -923,6 +949,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     p.res_coff = a->res.coff;
     p.res_c = a->res.c;
 
+    if (g_dbg_buf && g_dbg_next < g_dbg_cap) p.dbg = g_dbg_buf + 16ll * g_dbg_next++;
     int grid = g_num_sms * ctas_per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
     YL_CUDA(launch_kernel(conv_tc_kernel, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
@@ -931,3 +958,13 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
 }
 
 }  // namespace yl
+
+// Debug aid (tools/timeline.py): subsequent conv_tc launches get consecutive 8-slot rows of `device_buf`
+// ([capacity][16] uint64) into which CTA 0 writes %globaltimer at: kernel start, prologue done, dependency wait
+// done, first operands landed, first accumulator ready, last store issued, staging drained, exit.
+extern "C" int yl_debug_timeline(unsigned long long* device_buf, int capacity) {
+    yl::g_dbg_buf = device_buf;
+    yl::g_dbg_cap = device_buf ? capacity : 0;
+    yl::g_dbg_next = 0;
+    return YL_OK;
+}

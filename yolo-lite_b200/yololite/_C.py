@@ -82,6 +82,7 @@ _PROTOTYPES = {
     "yl_last_error_string": (C.c_char_p, []),
     "yl_init": (C.c_int, [C.c_int]),
     "yl_set_pdl": (C.c_int, [C.c_int]),
+    "yl_debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "yl_fold_bn_pack": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "yl_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.c_void_p]),
     "yl_nhwc_to_nchw": (C.c_int, [C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
