@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the bs=1 latency measurement")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="batches in flight per GPU (each on its own stream with its own plan buffers)")
     return ap.parse_args()
 
 
@@ -211,6 +214,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     from yololite import _C
+    from yololite.utils import dist as ydist
     from yololite.utils import ops
 
     _C.init(dev)
@@ -220,12 +224,33 @@ def main():
     host = [t.pin_memory() for t in synth_images(a.batch, n_sets, seed=rank)]
     devx = [t.to(dev) for t in host]
 
-    def step(x):
-        y, _ = model.infer(x)
+    n_fly = max(1, a.inflight)
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(n_fly)]
+
+    def step(x, slot=0):
+        y, _ = model.infer(x, slot=slot)
         return ops.nms_padded(y, CONF, IOU, None, False, False, MAX_DET)
 
-    for i in range(max(a.warmup, 3)):
-        dets, counts = step(devx[i % n_sets])
+    def run_steps(k, fly):
+        """k steps with `fly` batches in flight: step i runs on lane i % fly (own stream, own plan slot), so the
+        small latency-bound layers of one batch overlap the large layers of the other.  fly == 1 is strictly
+        serial on the current stream."""
+        if fly == 1:
+            for i in range(k):
+                out = step(devx[i % n_sets], 0)
+            return out
+        main = torch.cuda.current_stream(dev)
+        for s_ in lanes[:fly]:
+            s_.wait_stream(main)
+        for i in range(k):
+            with torch.cuda.stream(lanes[i % fly]):
+                out = step(devx[i % n_sets], i % fly)
+        for s_ in lanes[:fly]:
+            main.wait_stream(s_)
+        return out
+
+    for fly in sorted({1, n_fly}):
+        dets, counts = run_steps(max(a.warmup, 3) * fly, fly)
     torch.cuda.synchronize(dev)
     plan = model._get_plan(devx[0].shape, dev)[0]
     launches_per_step = plan.n_launches + 2                 # + nms_filter + nms_select
@@ -235,21 +260,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- timed region: K steps, CUDA events on the launching (current) stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    def timed(k, fly):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for i in range(a.steps):
-            dets, counts = step(devx[i % n_sets])
+        out = run_steps(k, fly)
         e1.record()
         barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        return ydist.max_over_ranks(e0.elapsed_time(e1), dev), out
+
+    # ---- timed region: K steps, CUDA events on the launching (current) stream, max over ranks
+    with ClockSampler(local) as clk:
+        ms_max, (dets, counts) = timed(a.steps, n_fly)
+    ms_serial = ms_max
+    if n_fly > 1:
+        ms_serial, _ = timed(a.steps, 1)
     n_det_local = int(counts.sum().item())
+
+    # ---- bs=1 latency (BASELINE metric: "bs1 p50 latency"): ingest + model + NMS + counts on the host
+    lat = None
+    if rank == 0 and not a.no_latency:
+        x1 = devx[0][:1].contiguous()
+        for _ in range(10):
+            step(x1)[1].tolist()
+        ts = []
+        for i in range(200):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            step(x1)[1].tolist()                            # host has the detection count = result delivered
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        lat = {"p50": round(ts[len(ts) // 2], 4), "p90": round(ts[int(len(ts) * 0.9)], 4), "min": round(ts[0], 4),
+               "unit": "ms", "what": f"{model_name} bs=1 640x640 device-resident input -> NMS'd count on host, 200 reps"}
 
     # ---- e2e through the public API, host tensors, H2D + D2H inside the timed region
     e2e = None
@@ -272,10 +314,7 @@ def main():
                 nd += len(r.boxes.data.cpu())               # device->host read of a result
         barrier()
         dt = time.perf_counter() - t0
-        te = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(a.batch * world * steps_e / float(te.item()), 1), "unit": "images/s",
+        e2e = {"value": round(a.batch * world * steps_e / ydist.max_over_ranks(dt, dev), 1), "unit": "images/s",
                "h2d_bytes_per_step": a.batch * 3 * IMG * IMG * 4, "d2h_bytes_per_step": a.batch * 4 + MAX_DET * 6 * 4,
                "steps": steps_e, "api": "YOLOLite.predict(pinned host fp32 BCHW tensor)"}
 
@@ -309,11 +348,9 @@ def main():
                 "tensor_frac": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3) / tf, 4)}
 
     # ---- detections gathered for the metric only (no collective on the hot path)
-    n_det = n_det_local
-    if dist is not None:
-        tt = torch.tensor([n_det_local], device=dev)
-        dist.all_reduce(tt)
-        n_det = int(tt.item())
+    gd, gc = ydist.gather_detections(dets, counts, total=a.batch * world)     # (B*world, 300, 6) + counts: 7.2 KB/img
+    n_det = int(gc.sum().item())
+    assert n_det == ydist.sum_over_ranks(n_det_local, dev)
 
     cpu_b = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -329,8 +366,11 @@ def main():
         line = {
             "metric": "images_per_sec", "value": round(total_images / (ms_max / 1e3), 1), "unit": "images/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_max / a.steps, 4),
+            "in_flight": n_fly, "value_serial": round(total_images / (ms_serial / 1e3), 1),
+            "bs1_latency_ms": lat,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "global_batch": a.batch * world, "parallelism": f"dp{world} batch-sharded, no collective",
+                       "in_flight": f"{n_fly} batches in flight per GPU (one stream + one plan slot each)",
                        "l2": f"{n_sets} rotating input batches of {a.batch * 3 * IMG * IMG * 4 / 1e6:.0f} MB each (> L2)",
                        "weights": "random init from cfg/yolo11.yaml, BN statistics randomised (seed 1)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * a.steps,

@@ -387,13 +387,25 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) YL_STAMP(1);
-    // everything above touched only constants (weights' bias, tensor maps); activations written by the
+    const int taps = p.ksize * p.ksize;
+    const int kiters = taps * p.cin_blocks;
+    // resident weights are constants too: their TMA loads are issued before the dependency wait, so they fly
+    // while the previous kernel of the stream is still draining
+    if (warp == 0 && (p.patch || p.wres) && elect_one()) {
+        mbar_expect_tx(w_bar, p.w_bytes);
+        if (p.patch) {
+            tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
+        } else {
+            int ki = 0;
+            for (int tap = 0; tap < taps; ++tap)
+                for (int cb = 0; cb < p.cin_blocks; ++cb, ++ki)
+                    tma_load_2d(sB + (size_t)ki * p.b_bytes, &p.tmB, w_bar, tap * p.ci_pad + cb * p.kblk, 0);
+        }
+    }
+    // everything above touched only constants (weights, bias, tensor maps); activations written by the
     // previous kernel of the stream are read / overwritten only after it has completed
     griddep_wait();
     if (threadIdx.x == 0) YL_STAMP(2);
-
-    const int taps = p.ksize * p.ksize;
-    const int kiters = taps * p.cin_blocks;
 
     // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
     // same coordinates / descriptors, so they live in uniform registers) and one elected lane issues the TMA /
@@ -405,10 +417,6 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         int st = 0;
         uint32_t ph = 0;  // ring position / phase of the stage being filled
         if (p.patch) {
-            if (leader) {
-                mbar_expect_tx(w_bar, p.w_bytes);
-                tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
-            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int mt = tile;
                 const int w0 = (mt % p.tiles_w) * p.TW;
@@ -426,13 +434,6 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
                 }
             }
         } else {
-            if (p.wres && leader) {
-                mbar_expect_tx(w_bar, p.w_bytes);
-                int ki = 0;
-                for (int tap = 0; tap < taps; ++tap)
-                    for (int cb = 0; cb < p.cin_blocks; ++cb, ++ki)
-                        tma_load_2d(sB + (size_t)ki * p.b_bytes, &p.tmB, w_bar, tap * p.ci_pad + cb * p.kblk, 0);
-            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 int mt = tile / p.n_tiles;

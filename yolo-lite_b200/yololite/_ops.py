@@ -218,13 +218,14 @@ def dfl_expectation(x: torch.Tensor, reg_max: int) -> torch.Tensor:
 
 
 class NmsWorkspace:
-    """Grow-only device scratch for yl_nms_batched, cached per device."""
+    """Grow-only device scratch for yl_nms_batched, cached per (device, stream): two batches in flight on two
+    streams must not share candidate lists."""
 
     _cache: dict = {}
 
     @classmethod
     def get(cls, nbytes: int, device) -> torch.Tensor:
-        key = (device.type, device.index)
+        key = (device.type, device.index, int(torch.cuda.current_stream(device).cuda_stream))
         t = cls._cache.get(key)
         if t is None or t.numel() < nbytes:
             t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

@@ -81,6 +81,9 @@ class DetectionPredictor:
     pipeline_chunks = 4
     #: never split below this many images per chunk (tiny plans waste the 148 SMs)
     pipeline_min_chunk = 8
+    #: chunks in flight on the GPU (1 or 2): consecutive chunks alternate between two streams / plan slots, so
+    #: the launch-latency-bound small layers of one chunk overlap the bandwidth-bound layers of the other
+    in_flight = 2
 
     def _chunking(self, im):
         """Number of ingest chunks for a host tensor batch (1 = plain path)."""
@@ -107,6 +110,7 @@ class DetectionPredictor:
                   "dets": torch.empty((B, a.max_det, 6), dtype=torch.float32, device=dev),
                   "counts": torch.empty((B,), dtype=torch.int32, device=dev),
                   "copy": torch.cuda.Stream(device=dev),
+                  "lanes": [torch.cuda.Stream(device=dev) for _ in range(2)],
                   "events": [torch.cuda.Event() for _ in range(n_chunks)]}
             self._pipe_state = st
         main = torch.cuda.current_stream(dev)
@@ -116,11 +120,21 @@ class DetectionPredictor:
                 st["buf"][k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
                 st["events"][k].record(st["copy"])
         model = self.model.model
+        fly = max(1, min(int(self.in_flight), n_chunks))
+        lanes = st["lanes"][:fly] if fly > 1 else [main]
+        for ln in lanes:
+            if ln is not main:
+                ln.wait_stream(main)
         for k in range(n_chunks):
-            main.wait_event(st["events"][k])
-            y, _ = model.infer(st["buf"][k * cb:(k + 1) * cb])
-            ops.nms_padded(y, a.conf, a.iou, a.classes, a.agnostic_nms, False, a.max_det,
-                           out=st["dets"][k * cb:(k + 1) * cb], counts=st["counts"][k * cb:(k + 1) * cb])
+            ln = lanes[k % fly]
+            with torch.cuda.stream(ln):
+                ln.wait_event(st["events"][k])
+                y, _ = model.infer(st["buf"][k * cb:(k + 1) * cb], slot=k % fly)
+                ops.nms_padded(y, a.conf, a.iou, a.classes, a.agnostic_nms, False, a.max_det,
+                               out=st["dets"][k * cb:(k + 1) * cb], counts=st["counts"][k * cb:(k + 1) * cb])
+        for ln in lanes:
+            if ln is not main:
+                main.wait_stream(ln)
         return st["buf"], st["dets"], st["counts"]
 
     def postprocess(self, preds, img, orig_imgs, nms_out=None):

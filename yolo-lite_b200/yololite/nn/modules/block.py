@@ -82,10 +82,48 @@ class C3(YLModule):
         self.cv3 = Conv(2 * c_, c2, 1)
         self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, k=((1, 1), (3, 3)), e=1.0) for _ in range(n)))
 
+    def _merged_pack(self):
+        """cv2 and cv1 read the same tensor: ONE 1x1 conv with the stacked weights [cv2; cv1] produces both, or
+        None when the two convs are not alike."""
+        from ... import _ops
+
+        a, b = self.cv1, self.cv2
+        ca, cb = a.conv, b.conv
+        same = (ca.kernel_size == cb.kernel_size == (1, 1) and ca.stride == cb.stride == (1, 1)
+                and ca.groups == cb.groups == 1 and ca.in_channels == cb.in_channels
+                and ca.out_channels == cb.out_channels and ca.out_channels % 8 == 0 and ca.bias is None
+                and cb.bias is None and type(a.act) is type(b.act) and hasattr(a, "bn") and hasattr(b, "bn")
+                and a.bn.eps == b.bn.eps)
+        if not same:
+            return None
+        pc = self.__dict__.get("_yl_pc12")
+        dev = ca.weight.device
+        if pc is None or pc.w.device != dev:
+            cat = lambda f: torch.cat([f(b), f(a)])  # noqa: E731  (cv2's rows first)
+            with torch.cuda.device(dev):
+                pc = _ops.pack_conv(cat(lambda m: m.conv.weight),
+                                    (cat(lambda m: m.bn.weight), cat(lambda m: m.bn.bias),
+                                     cat(lambda m: m.bn.running_mean), cat(lambda m: m.bn.running_var), a.bn.eps),
+                                    None, device=dev)
+            self.__dict__["_yl_pc12"] = pc
+        return pc
+
     def _emit(self, g, x, out=None):
+        from ._emit import act_flag
+
         c_ = self.cv1.conv.out_channels
-        cat = g.alloc(x.n, x.h, x.w, 2 * c_)
         blocks = list(self.m)
+        pc12 = self._merged_pack() if blocks else None
+        if pc12 is not None:
+            # channels [0, c_) = m(cv1(x)), [c_, 2c_) = cv2(x), [2c_, 3c_) = cv1(x): the merged conv fills the
+            # upper two slices in one launch, cv3 reads the lower two
+            buf = g.alloc(x.n, x.h, x.w, 3 * c_)
+            g.conv(g.mat(x), pc12, 1, act=act_flag(self.cv1.act), out=buf.slice(c_, 2 * c_))
+            y = buf.slice(2 * c_, c_)
+            for i, b in enumerate(blocks):
+                y = b._emit(g, y, out=buf.slice(0, c_) if i == len(blocks) - 1 else None)
+            return self.cv3._emit(g, buf.slice(0, 2 * c_), out=out)
+        cat = g.alloc(x.n, x.h, x.w, 2 * c_)
         y = self.cv1._emit(g, x, out=None if blocks else cat.slice(0, c_))
         for i, b in enumerate(blocks):
             y = b._emit(g, y, out=cat.slice(0, c_) if i == len(blocks) - 1 else None)

@@ -283,9 +283,9 @@ class BaseModel(YLModule):
         memo[k] = c
         return c
 
-    def _get_plan(self, shape, dev, want_raw=False):
+    def _get_plan(self, shape, dev, want_raw=False, slot=0):
         plans = self.__dict__.setdefault("_yl_plans", {})
-        key = (tuple(shape), dev.index, bool(self.use_cuda_graph), bool(want_raw))
+        key = (tuple(shape), dev.index, bool(self.use_cuda_graph), bool(want_raw), int(slot))
         entry = plans.get(key)
         if entry is None:
             with torch.cuda.device(dev):
@@ -303,8 +303,12 @@ class BaseModel(YLModule):
         return entry
 
     @torch.no_grad()
-    def infer(self, x: torch.Tensor, want_raw: bool = False):
+    def infer(self, x: torch.Tensor, want_raw: bool = False, slot: int = 0):
         """Engine entry: NCHW float image batch on CUDA -> (y (B, 4+nc, A) fp32, [raw (B, no, H, W) views]).
+
+        `slot` selects one of several independent plans (own activation buffers and CUDA graph) for the same
+        shape, so a caller can keep two batches in flight on two streams: the launch-latency-bound small layers
+        of one batch then overlap the bandwidth-bound large layers of the other.
 
         The raw head maps are only needed by callers of the module-level API (`forward`); the engine path
         (`want_raw=False`) gets an empty list and the plan never writes them.  The returned tensors alias the
@@ -321,7 +325,7 @@ class BaseModel(YLModule):
         s = int(self.stride.max()) if hasattr(self, "stride") else 32
         if x.shape[2] % s or x.shape[3] % s:
             raise ValueError(f"image size {tuple(x.shape[2:])} must be a multiple of the model stride {s}")
-        plan, static_in, y, raws = self._get_plan(x.shape, dev, want_raw)
+        plan, static_in, y, raws = self._get_plan(x.shape, dev, want_raw, slot)
         with torch.cuda.device(dev):
             if x.dtype == torch.float32 and x.is_contiguous():
                 plan.run(ingest_ptr=x.data_ptr())          # zero-copy: the ingest kernel reads x directly
