@@ -188,6 +188,22 @@ int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream);
  * {gain, padx, pady, w0, h0}. */
 int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream);
 
+/* ---- image preprocess (the step before the path) ---------------------------------------------- */
+/* One source image of a letterbox batch: HWC uint8 BGR on the DEVICE, `pitch` bytes per row; it is resized to
+ * (new_w, new_h) with cv2's 8-bit INTER_LINEAR arithmetic (skipped when the size already matches) and placed
+ * at (left, top) of the output canvas. */
+typedef struct yl_lb_image {
+    const uint8_t* src;
+    int32_t sh, sw, pitch;
+    int32_t new_w, new_h, left, top;
+    int32_t _pad;
+} yl_lb_image;
+/* LetterBox + BGR->RGB + HWC->CHW + float + /255 (data/augment.py:612-681, engine/predictor.py:67-85) for n
+ * images into dst_nchw (n,3,H,W) fp32; canvas pixels outside an image get pad_value/255 (the reference pads
+ * with 114).  Bit-exact against cv2.resize(INTER_LINEAR) + copyMakeBorder + the float conversion on the CPU.
+ * imgs_dev: n descriptors in DEVICE memory. */
+int yl_letterbox_u8(const yl_lb_image* imgs_dev, int n, float* dst_nchw, int H, int W, int pad_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,8 @@ Fixtures (all seeded; weights are the name-keyed values of oracle/weights.py, so
                             PSABlock, C2PSA, Detect, DFL) on small inputs
   nms_torchvision.npz       torchvision.ops.nms (CPU, the arithmetic behind ops.py:265) known-answer cases
   nms_reference.npz         reference ops.non_max_suppression (max_time_img=1e9) on synthetic predictions
+  letterbox.npz             reference LetterBox (data/augment.py:612-681) + predictor.preprocess arithmetic
+                            (engine/predictor.py:67-85) on seeded uint8 images (only seeds + outputs stored)
 """
 from __future__ import annotations
 
@@ -180,9 +182,51 @@ def gen_nms_reference():
     np.savez_compressed(GOLD / "nms_reference.npz", **out)
 
 
+LETTERBOX_CASES = [
+    # (src h, src w, new_shape, auto, scaleup, seed)
+    (97, 131, (64, 64), False, True, 1),      # downscale, wide
+    (131, 97, (64, 96), False, True, 2),      # downscale, tall, rectangular target
+    (23, 31, (64, 64), False, True, 3),       # upscale
+    (23, 31, (64, 64), False, False, 4),      # scaleup=False: no resize, centre pad
+    (64, 64, (64, 64), False, True, 5),       # identity
+    (120, 200, (128, 128), True, True, 6),    # auto=True: minimal-rectangle padding (mod stride)
+    (200, 120, (128, 128), True, True, 7),
+    (128, 256, (64, 64), False, True, 8),     # exact 2x / 4x downscale
+    (1, 50, (32, 32), False, True, 9),        # degenerate one-row image
+]
+
+
+def letterbox_image(h, w, seed):
+    return np.random.default_rng(1000 + seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def gen_letterbox():
+    import_reference()
+    from yololite.data.augment import LetterBox
+
+    out = {"n_cases": np.array(len(LETTERBOX_CASES))}
+    for i, (h, w, new_shape, auto, scaleup, seed) in enumerate(LETTERBOX_CASES):
+        img = letterbox_image(h, w, seed)
+        lb = LetterBox(new_shape, auto=auto, scaleup=scaleup, stride=32)(image=img)
+        # predictor.preprocess (engine/predictor.py:76-84): stack, BGR->RGB, BHWC->BCHW, float, /255
+        im = np.stack([lb])
+        im = im[..., ::-1].transpose((0, 3, 1, 2))
+        im = np.ascontiguousarray(im)
+        t = torch.from_numpy(im).float()
+        t /= 255
+        out[f"lb_{i}"] = lb
+        out[f"pre_{i}"] = t.numpy()
+    np.savez_compressed(GOLD / "letterbox.npz", **out)
+    print("letterbox.npz", len(LETTERBOX_CASES), "cases")
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-letterbox" in sys.argv:
+        gen_letterbox()
+        sys.exit(0)
+    gen_letterbox()
     gen_nms_torchvision()
     gen_nms_reference()
     gen_modules()

@@ -151,6 +151,13 @@ int launch_conv_direct(const yl_conv_args* a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 struct DwParams {
     const __nv_bfloat16* x;
     long long x_cstride;
@@ -270,6 +277,172 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
     }
 }
 
+
+// Depthwise 3x3 on the (legacy) tensor-core path.  The strip kernel above is instruction-issue bound (ncu: ~50
+// thread instructions per output element, mostly bf16->fp32 unpacking and FMAs, issue slots 70 % busy at 1.8
+// TB/s).  Here 16 pixels x 8 channels are one m16n8k16 mma.sync step chain with K = (tap pair) x (8 channels)
+// and a B operand that is diagonal in the channel: D[px, c] = sum_tap x[px + tap, c] * w[tap, c].  7/8 of the
+// multiplies hit zeros, but 5 MMAs replace 144 FMAs + ~200 unpack instructions.
+//   block = (8 x 16)-pixel tile of one image x up to 8 channel groups; a warp owns TWO adjacent groups;
+//   smem  = the 10 x 18 halo patch, stored [group][row][col] as 16-byte pixels so that an A fragment word is
+//           one conflict-free 32-bit load (lanes g = 8 consecutive pixels, t = word of the pixel);
+//   a patch row feeds three output rows: the fragments live in a rolling 3-row register window, so each
+//           output row costs 6 shared loads per group instead of 18 (the first version was L1-wavefront bound);
+//   the results of the two groups are transposed inside each lane quad (4 shuffles) so a lane stores 16 bytes
+//           and a quad writes 2 x 32 contiguous bytes: full sectors, half the store wavefronts.
+template <bool ACT, bool ADD>
+__global__ void __launch_bounds__(128) dwconv3x3_mma_kernel(const DwParams p, int tiles_w, int ngrp, int gstride) {
+    constexpr int TH = 8, TW = 16, PH = TH + 2, PW = TW + 2;
+    extern __shared__ uint4 dw_patch[];  // [ngrp][gstride] pixels of 8 channels
+    griddep_launch_dependents();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int w0 = ((int)blockIdx.x % tiles_w) * TW;
+    const int h0 = ((int)blockIdx.x / tiles_w) * TH;
+    const int cg0 = blockIdx.y * ngrp;            // first channel group of this block
+    const int n = blockIdx.z;
+    const int ng = min(ngrp, (p.C >> 3) - cg0);   // groups really present (the last block may be short)
+    const int myg = 2 * warp;                     // this warp's first group within the block
+    const bool has_a = myg < ng, has_b = myg + 1 < ng;
+
+    // ---- constants first (they overlap the previous kernel's tail under PDL): the diagonal B fragments
+    uint32_t bq[2][5][2];
+    float bia[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const bool has = q ? has_b : has_a;
+        const int c0 = (cg0 + myg + q) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int tap = 2 * ks + hh;
+                uint32_t v = 0;
+                if (has && tap < 9 && (g >> 1) == t) {
+                    const uint32_t wbits = (uint32_t)__bfloat16_as_ushort(p.w[tap * p.C + c0 + g]);
+                    v = (g & 1) ? (wbits << 16) : wbits;   // k = 2t (+1): low / high half of the register
+                }
+                bq[q][ks][hh] = v;
+            }
+        bia[q][0] = has ? __ldg(p.bias + c0 + 2 * t) : 0.f;
+        bia[q][1] = has ? __ldg(p.bias + c0 + 2 * t + 1) : 0.f;
+    }
+    griddep_wait();
+
+    // ---- stage the halo patch with asynchronous 16-byte copies (zero-filled where the pixel is padding):
+    // consecutive threads take consecutive channel groups of one pixel, i.e. whole pixels, coalesced
+    constexpr int npix = PH * PW;
+    {
+        const uint32_t patch_s = smem_u32(dw_patch);
+        const __nv_bfloat16* src0 = p.x + (long long)n * p.H * p.W * p.x_cstride + p.x_coff + cg0 * 8;
+        for (int idx = threadIdx.x; idx < npix * ng; idx += blockDim.x) {
+            const int pix = idx / ng, cg = idx - pix * ng;
+            const int pr = pix / PW, pc = pix - pr * PW;
+            const int hi = h0 - 1 + pr, wi = w0 - 1 + pc;
+            const bool ok = hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            const int off = ok ? (hi * p.W + wi) : 0;   // < 2^31 pixels per image (checked by the launcher)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(patch_s + (uint32_t)(cg * gstride + pix) * 16u),
+                         "l"(src0 + (long long)off * p.x_cstride + cg * 8), "r"(ok ? 16 : 0)
+                         : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!has_a) return;
+
+    // every smem offset below is a compile-time constant relative to rp0 / rp1
+    const uint32_t* rp0 = reinterpret_cast<const uint32_t*>(dw_patch + myg * gstride) + g * 4 + t;
+    const uint32_t* rp1 = rp0 + (has_b ? gstride * 4 : 0);
+    // after the quad transpose lane t stores: pixel g + 8 * (t >> 1), group myg + (t & 1)
+    const int spx = w0 + g + 8 * (t >> 1);
+    const bool st_ok = spx < p.W && ((t & 1) == 0 || has_b);
+    const long long pixs = ((long long)n * p.H + h0) * p.W + spx;
+    char* yp = reinterpret_cast<char*>(p.y + pixs * p.y_cstride + p.y_coff + (cg0 + myg + (t & 1)) * 8);
+    const long long y_row = (long long)p.W * p.y_cstride * 2;
+    // residual (ADD) is read in the accumulator layout: pixel g (+8), channels 2t, 2t+1 of each group
+    const long long pixa = ((long long)n * p.H + h0) * p.W + w0 + g;
+    const char* ap = ADD ? reinterpret_cast<const char*>(p.add + pixa * p.add_cstride + p.add_coff + (cg0 + myg) * 8 + 2 * t)
+                         : nullptr;
+    const long long a_row = (long long)p.W * p.add_cstride * 2, a_half = 16 * p.add_cstride;
+    const bool ok0 = w0 + g < p.W, ok1 = w0 + g + 8 < p.W;
+    const int rows = min(TH, p.H - h0);
+
+    uint32_t win[2][3][3][2];   // [group][patch row % 3][dc][pixel half]
+#define YL_DW_LOADROW(PR_)                                                   \
+    _Pragma("unroll") for (int dc = 0; dc < 3; ++dc) {                        \
+        win[0][(PR_) % 3][dc][0] = rp0[((PR_) * PW + dc) * 4];                \
+        win[0][(PR_) % 3][dc][1] = rp0[((PR_) * PW + dc + 8) * 4];            \
+        win[1][(PR_) % 3][dc][0] = rp1[((PR_) * PW + dc) * 4];                \
+        win[1][(PR_) % 3][dc][1] = rp1[((PR_) * PW + dc + 8) * 4];            \
+    }
+    YL_DW_LOADROW(0)
+    YL_DW_LOADROW(1)
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        if (r < rows) {
+            YL_DW_LOADROW(r + 2)
+            float acc[2][4];
+            uint32_t av[2][2] = {{0u, 0u}, {0u, 0u}};
+            if (ADD) {
+                if (ok0) av[0][0] = __ldg(reinterpret_cast<const uint32_t*>(ap));
+                if (ok1) av[0][1] = __ldg(reinterpret_cast<const uint32_t*>(ap + a_half));
+                if (has_b) {
+                    if (ok0) av[1][0] = __ldg(reinterpret_cast<const uint32_t*>(ap + 16));
+                    if (ok1) av[1][1] = __ldg(reinterpret_cast<const uint32_t*>(ap + a_half + 16));
+                }
+                ap += a_row;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                acc[q][0] = bia[q][0]; acc[q][1] = bia[q][1]; acc[q][2] = bia[q][0]; acc[q][3] = bia[q][1];
+#pragma unroll
+                for (int ks = 0; ks < 5; ++ks) {
+                    uint32_t a[4];
+                    {
+                        const int tap = 2 * ks, dr = tap / 3, dc = tap - 3 * dr;
+                        a[0] = win[q][(r + dr) % 3][dc][0];
+                        a[1] = win[q][(r + dr) % 3][dc][1];
+                    }
+                    if (ks < 4) {
+                        const int tap = 2 * ks + 1, dr = tap / 3, dc = tap - 3 * dr;
+                        a[2] = win[q][(r + dr) % 3][dc][0];
+                        a[3] = win[q][(r + dr) % 3][dc][1];
+                    } else {
+                        a[2] = 0u;
+                        a[3] = 0u;
+                    }
+                    mma_bf16_16816(acc[q], a, bq[q][ks][0], bq[q][ks][1]);
+                }
+                if (ACT) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[q][i] = silu_fast(acc[q][i]);
+                }
+                if (ADD) {
+                    acc[q][0] += bf16lo_f(av[q][0]); acc[q][1] += bf16hi_f(av[q][0]);
+                    acc[q][2] += bf16lo_f(av[q][1]); acc[q][3] += bf16hi_f(av[q][1]);
+                }
+            }
+            // items: 0 = (pixel g, group A), 1 = (pixel g, group B), 2 = (pixel g+8, A), 3 = (pixel g+8, B); lane t
+            // holds word t of every item -> 4x4 transpose inside the quad -> lane t holds the 16 bytes of item t
+            uint32_t v0 = pack_bf16x2(acc[0][0], acc[0][1]), v1 = pack_bf16x2(acc[1][0], acc[1][1]);
+            uint32_t v2 = pack_bf16x2(acc[0][2], acc[0][3]), v3 = pack_bf16x2(acc[1][2], acc[1][3]);
+            {
+                const uint32_t s0 = (t & 1) ? v0 : v1, s1 = (t & 1) ? v2 : v3;
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                if (t & 1) { v0 = r0; v2 = r1; } else { v1 = r0; v3 = r1; }
+            }
+            {
+                const uint32_t s0 = (t & 2) ? v0 : v2, s1 = (t & 2) ? v1 : v3;
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+                if (t & 2) { v0 = r0; v1 = r1; } else { v2 = r0; v3 = r1; }
+            }
+            if (st_ok) *reinterpret_cast<uint4*>(yp) = make_uint4(v0, v1, v2, v3);
+            yp += y_row;
+        }
+    }
+#undef YL_DW_LOADROW
+}
+
 // ------------------------------------------------------------------------------------------------ BN fold + pack
 __global__ void fold_pack_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* __restrict__ mean,
@@ -367,13 +540,39 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
     p.C = x->c;
     p.act = act;
     YL_CHECK(x->n <= 65535, YL_ERR_ARG, "batch too large for one launch");
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        const char* em = getenv("YL_DW_MMA");
+        if (!(em && *em && atoi(em) == 0)) {
+            // tensor-core path: (8 x 16)-pixel tiles, up to 8 channel groups per block, two groups per warp
+            const int groups = x->c / 8;
+            const int cblocks = yl::ceil_div(groups, 8);
+            int ngrp = yl::ceil_div(groups, cblocks);
+            ngrp += ngrp & 1;                                      // even: warps own whole pairs
+            const int npix = 10 * 18;
+            const int gstride = npix + ((1 - npix) % 8 + 8) % 8;  // = 1 (mod 8): groups land 4 banks apart
+            const int tiles_w = yl::ceil_div(x->w, 16), tiles_h = yl::ceil_div(x->h, 8);
+            const dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)yl::ceil_div(groups, ngrp), (unsigned)x->n);
+            const dim3 block(32 * (ngrp / 2));
+            const size_t smem = (size_t)ngrp * gstride * 16;
+#define YL_DWM(ACT_, ADD_) \
+    YL_CUDA(yl::launch_kernel(yl::dwconv3x3_mma_kernel<ACT_, ADD_>, grid, block, smem, s, p, tiles_w, ngrp, gstride))
+            if (act) {
+                if (p.add) YL_DWM(true, true); else YL_DWM(true, false);
+            } else {
+                if (p.add) YL_DWM(false, true); else YL_DWM(false, false);
+            }
+#undef YL_DWM
+            YL_LAUNCH_OK("dwconv3x3_mma_kernel");
+            return YL_OK;
+        }
+    }
     const char* e = getenv("YL_DW_STRIP");  // launch-time only (plans are captured into CUDA graphs)
     const int strip = (e && *e) ? atoi(e) : 2;  // measured: 2-pixel strips are fastest (tools/bench_kernels.py)
     const int P = strip >= 4 ? 4 : (strip >= 2 ? 2 : 1);
     const long long per_image = (long long)x->h * yl::ceil_div(x->w, P) * (x->c / 8);
     YL_CHECK(per_image < (1ll << 31), YL_ERR_ARG, "image too large");
     const dim3 grid((unsigned)yl::ceil_div64(per_image, 256), (unsigned)x->n, 1), block(256);
-    cudaStream_t s = (cudaStream_t)stream;
     if (P == 4) YL_CUDA(yl::launch_kernel(yl::dwconv3x3_kernel<4>, grid, block, 0, s, p));
     else if (P == 2) YL_CUDA(yl::launch_kernel(yl::dwconv3x3_kernel<2>, grid, block, 0, s, p));
     else YL_CUDA(yl::launch_kernel(yl::dwconv3x3_kernel<1>, grid, block, 0, s, p));
@@ -397,13 +596,6 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
 // fp32).  A warp walks the 64 output pixels of one row in four 16-pixel steps; the weight (B) fragments and
 // biases stay in registers for the whole walk.
 namespace yl {
-
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 constexpr int kStemRowPixels = 64;  // output pixels of one row per warp
 constexpr int kStemWarps = 8;       // output rows per block

@@ -55,6 +55,7 @@ struct ConvTcParams {
     // CTA into smem [kiter][co_tile][kblk]; the ring then carries activations only (TMA issue rate, not bytes, is
     // what bounds the thin layers: ~3.3 clk per box row per SM, tools/tma_bench.cu)
     int wres;
+    int wearly;                  // issue the resident-weight loads before the PDL dependency wait
     uint32_t tmem_cols;
     uint32_t a_bytes, b_bytes;   // per-stage smem footprint (1024-aligned)
     uint32_t b_region;           // smem bytes of the weight area: ring (stages * b_bytes) or resident block
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     const int kiters = taps * p.cin_blocks;
     // resident weights are constants too: their TMA loads are issued before the dependency wait, so they fly
     // while the previous kernel of the stream is still draining
-    if (warp == 0 && (p.patch || p.wres) && elect_one()) {
+    if (warp == 0 && p.wearly && (p.patch || p.wres) && elect_one()) {
         mbar_expect_tx(w_bar, p.w_bytes);
         if (p.patch) {
             tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
@@ -406,6 +407,17 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     // previous kernel of the stream are read / overwritten only after it has completed
     griddep_wait();
     if (threadIdx.x == 0) YL_STAMP(2);
+    if (warp == 0 && !p.wearly && (p.patch || p.wres) && elect_one()) {
+        mbar_expect_tx(w_bar, p.w_bytes);
+        if (p.patch) {
+            tma_load_3d(sB, &p.tmW3, w_bar, 0, 0, 0);
+        } else {
+            int ki = 0;
+            for (int tap = 0; tap < taps; ++tap)
+                for (int cb = 0; cb < p.cin_blocks; ++cb, ++ki)
+                    tma_load_2d(sB + (size_t)ki * p.b_bytes, &p.tmB, w_bar, tap * p.ci_pad + cb * p.kblk, 0);
+        }
+    }
 
     // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
     // same coordinates / descriptors, so they live in uniform registers) and one elected lane issues the TMA /
@@ -942,6 +954,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
         p.det_stride = a->det.stride;
         p.det_M = (long long)x.n * x.h * x.w;
     }
+    p.wearly = env_int("YL_WEARLY", 1);
     p.bias = a->bias;
     p.n_bias = a->co_pad;
     p.act = a->act;
@@ -951,7 +964,7 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     p.res_c = a->res.c;
 
     if (g_dbg_buf && g_dbg_next < g_dbg_cap) p.dbg = g_dbg_buf + 16ll * g_dbg_next++;
-    int grid = g_num_sms * ctas_per_sm;
+    int grid = g_num_sms * (ctas_per_sm < env_int("YL_GRID_CTAS", 2) ? ctas_per_sm : env_int("YL_GRID_CTAS", 2));
     if (grid > p.total_tiles) grid = p.total_tiles;
     YL_CUDA(launch_kernel(conv_tc_kernel, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
     YL_LAUNCH_OK("conv_tc_kernel");

@@ -57,6 +57,22 @@ class DetEpilogue(C.Structure):
 DET_NONE, DET_BOX, DET_CLS = 0, 1, 2
 
 
+class LbImage(C.Structure):
+    """Mirror of `yl_lb_image` (40 bytes)."""
+
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("sh", C.c_int32),
+        ("sw", C.c_int32),
+        ("pitch", C.c_int32),
+        ("new_w", C.c_int32),
+        ("new_h", C.c_int32),
+        ("left", C.c_int32),
+        ("top", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [
         ("x", Tensor),
@@ -109,6 +125,7 @@ _PROTOTYPES = {
                                C.c_void_p, C.c_void_p]),
     "yl_xywh2xyxy_inplace": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "yl_scale_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "yl_letterbox_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

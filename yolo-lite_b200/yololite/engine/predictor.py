@@ -65,9 +65,19 @@ class DetectionPredictor:
         return [letterbox(image=x) for x in im]
 
     def preprocess(self, im):
-        """BCHW float tensor: `.to(device).float()`.  list of HWC BGR uint8: letterbox, BGR->RGB, /255."""
+        """BCHW float tensor: `.to(device).float()`.  list of HWC BGR uint8 images: LetterBox, BGR->RGB, HWC->CHW,
+        float, /255 as ONE CUDA kernel over the raw bytes (bit-exact against the reference's cv2 path): the upload
+        is the uint8 pixels, 4x fewer PCIe bytes than the fp32 batch of the reference (predictor.py:67-85)."""
         if isinstance(im, torch.Tensor):
             return im.to(self.device, non_blocking=True).float()
+        same_shapes = len({x.shape for x in im}) == 1
+        if all(isinstance(x, np.ndarray) and x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 3 for x in im):
+            from ..data.augment import _Staging, letterbox_batch_cuda
+
+            if getattr(self, "_lb_staging", None) is None:
+                self._lb_staging = _Staging()
+            return letterbox_batch_cuda(im, self.imgsz, auto=same_shapes and self.model.pt, stride=self.model.stride,
+                                        device=self.device, staging=self._lb_staging)
         arr = np.stack(self.pre_transform(im))
         arr = np.ascontiguousarray(arr[..., ::-1].transpose((0, 3, 1, 2)))
         t = torch.from_numpy(arr).to(self.device, non_blocking=True).float()
