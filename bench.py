@@ -308,15 +308,59 @@ def main():
         barrier()
         t0 = time.perf_counter()
         nd = 0
+        prev = None
         for i in range(steps_e):
-            res = yl.predict(host[i % n_sets], **kw)
-            for r in res[:1]:
-                nd += len(r.boxes.data.cpu())               # device->host read of a result
+            res = yl.predict(host[i % n_sets], **kw)        # asynchronous: upload + kernels are only enqueued
+            if prev is not None:
+                nd += len(prev[0].boxes.data.cpu())         # device->host read of the PREVIOUS step's result
+            prev = res
+        nd += len(prev[0].boxes.data.cpu())
         barrier()
         dt = time.perf_counter() - t0
         e2e = {"value": round(a.batch * world * steps_e / ydist.max_over_ranks(dt, dev), 1), "unit": "images/s",
                "h2d_bytes_per_step": a.batch * 3 * IMG * IMG * 4, "d2h_bytes_per_step": a.batch * 4 + MAX_DET * 6 * 4,
-               "steps": steps_e, "api": "YOLOLite.predict(pinned host fp32 BCHW tensor)"}
+               "steps": steps_e, "api": "YOLOLite.predict(pinned host fp32 BCHW tensor); every step's Results are read on the host, one "
+                      "step behind the upload of the next batch (predict() is asynchronous, Results resolve lazily)"}
+
+    # ---- image preprocess: uint8 HWC BGR images -> letterboxed fp32 NCHW batch on the GPU
+    prep = None
+    if rank == 0 and not a.no_e2e:
+        import numpy as np
+
+        from yololite.data import letterbox_batch_cuda
+        from yololite.data.augment import _Staging
+
+        rng = np.random.default_rng(0)
+        imgs = [rng.integers(0, 256, (1080, 810, 3), dtype=np.uint8) for _ in range(a.batch)]
+        stg = _Staging()
+        out = letterbox_batch_cuda(imgs, (IMG, IMG), auto=True, stride=32, device=dev, staging=stg)
+        torch.cuda.synchronize(dev)
+        from yololite import _C as _c
+
+        descs_dev = stg.dev                                   # descriptors + pixels are already resident
+        ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        ek0.record()
+        for _ in range(reps):
+            _c.check(_c.load().yl_letterbox_u8(descs_dev.data_ptr(), a.batch, out.data_ptr(), out.shape[2], out.shape[3],
+                                               114, _c.stream_ptr()), "yl_letterbox_u8")
+        ek1.record()
+        torch.cuda.synchronize(dev)
+        k_ms = ek0.elapsed_time(ek1) / reps
+        byts = a.batch * (1080 * 810 * 3 + out.shape[1] * out.shape[2] * out.shape[3] * 4)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            letterbox_batch_cuda(imgs, (IMG, IMG), auto=True, stride=32, device=dev, staging=stg, out=out)
+        torch.cuda.synchronize(dev)
+        host_ms = (time.perf_counter() - t0) / 3 * 1e3
+        hbm_pk = peaks()[0]
+        prep = {"kernel": "letterbox_u8", "workload": f"{a.batch} x 1080x810 BGR uint8 -> {tuple(out.shape)} fp32",
+                "kernel_ms": round(k_ms, 4), "kernel_images_per_s": round(a.batch / k_ms * 1e3, 1),
+                "algorithmic_GBps": round(byts / 1e9 / (k_ms / 1e3), 1), "hbm_frac": round(byts / 1e9 / (k_ms / 1e3) / hbm_pk, 4),
+                "from_host_ms": round(host_ms, 3), "from_host_images_per_s": round(a.batch / host_ms * 1e3, 1),
+                "h2d_bytes": a.batch * 1080 * 810 * 3,
+                "note": "from_host = pinned pack + one H2D + kernel (host memcpy bound)"}
+        del imgs, out
 
     # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager pass
     roof, breakdown = None, None
@@ -375,7 +419,7 @@ def main():
                        "weights": "random init from cfg/yolo11.yaml, BN statistics randomised (seed 1)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
             "launches_per_step": launches_per_step, "detections_last_step": n_det,
-            "roofline": roof, "cpu_baseline": cpu_b, "kernel_breakdown": breakdown,
+            "roofline": roof, "preprocess": prep, "cpu_baseline": cpu_b, "kernel_breakdown": breakdown,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -188,6 +188,19 @@ int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream);
  * {gain, padx, pady, w0, h0}. */
 int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream);
 
+/* ---- fused C3k2 tail ----------------------------------------------------------------------------------------- */
+/* Everything after cv1 of a C3k2 / C2f block with ONE plain Bottleneck (nn/modules/block.py:231-235, 330-343,
+ * 720-728): t = cv1(x) = [y0 | y1] (2c channels) ->
+ *     h = SiLU(conv3x3_a(y1)) (c -> c/2);  y2 = [y1 +] SiLU(conv3x3_b(h)) (c/2 -> c);
+ *     y = SiLU(conv1x1_2([y0, y1, y2])) (3c -> c2)
+ * in one kernel: h and y2 never leave shared memory (bf16, the same rounding points as the layer-by-layer path).
+ * wa / wb / w2 are yl_fold_bn_pack outputs ([co_pad][k*k*ci_pad] bf16) with their fp32 biases.
+ * yl_c3k2_tail_supported(c, c2): built for c in {16, 32}, c2 in {32, 64, 128, 256}. */
+int yl_c3k2_tail_supported(int c, int c2);
+int yl_c3k2_tail(const yl_tensor* t, const yl_tensor* y, const void* wa, const float* ba, int wa_co_pad, int wa_ci_pad,
+                 const void* wb, const float* bb, int wb_ci_pad, const void* w2, const float* b2, int w2_ci_pad,
+                 int shortcut, void* stream);
+
 /* ---- image preprocess (the step before the path) ---------------------------------------------- */
 /* One source image of a letterbox batch: HWC uint8 BGR on the DEVICE, `pitch` bytes per row; it is resized to
  * (new_w, new_h) with cv2's 8-bit INTER_LINEAR arithmetic (skipped when the size already matches) and placed

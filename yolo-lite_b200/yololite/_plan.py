@@ -202,6 +202,21 @@ class Builder:
                    reads=(x, res), writes=(y if store else None, y_up))
         return y if store else None
 
+    def c3k2_tail(self, t: View, pa: PackedConv, pb: PackedConv, p2: PackedConv, shortcut: bool, out=None) -> View:
+        """Fused [Bottleneck(3x3, 3x3) + C2f.cv2] on t = cv1(x) = [y0 | y1] (see yl_c3k2_tail)."""
+        y = self._out(out, t.n, t.h, t.w, p2.co)
+        tt, yt = t.ct(), y.ct()
+        c = t.c // 2
+        px = t.n * t.h * t.w
+        self._push(self.lib.yl_c3k2_tail, C.byref(tt), C.byref(yt), pa.w.data_ptr(), pa.bias.data_ptr(), pa.co_pad,
+                   pa.ci_pad, pb.w.data_ptr(), pb.bias.data_ptr(), pb.ci_pad, p2.w.data_ptr(), p2.bias.data_ptr(),
+                   p2.ci_pad, int(bool(shortcut)), keep=(tt, yt, pa, pb, p2), kind="c3k2_tail",
+                   bytes_=px * (t.c + p2.co) * 2 + (pa.w.numel() + pb.w.numel() + p2.w.numel()) * 2,
+                   flops=2 * px * (9 * c * (c // 2) * 2 + 3 * c * p2.co),
+                   desc=f"[{c}->{c // 2} k3, {c // 2}->{c} k3{' +res' if shortcut else ''}, {3 * c}->{p2.co} k1] "
+                        f"{t.h}x{t.w}", reads=(t,), writes=(y,))
+        return y
+
     def sppf_pool(self, x: View, y1: View, y2: View, y3: View, k: int):
         ts = [v.ct() for v in (x, y1, y2, y3)]
         self._push(self.lib.yl_sppf_pool, *[C.byref(t) for t in ts], k, keep=tuple(ts), kind="sppf_pool",

@@ -23,7 +23,7 @@ from ..data import LetterBox, load_inference_source
 from ..nn.autobackend import AutoBackend
 from ..utils import LOGGER, ops
 from ..utils.torch_utils import select_device, smart_inference_mode
-from .results import Results
+from .results import BatchDetections, Results
 
 
 class _LazyTensorImage:
@@ -74,10 +74,9 @@ class DetectionPredictor:
         if all(isinstance(x, np.ndarray) and x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 3 for x in im):
             from ..data.augment import _Staging, letterbox_batch_cuda
 
-            if getattr(self, "_lb_staging", None) is None:
-                self._lb_staging = _Staging()
+            stg = self.model.__dict__.setdefault("_yl_lb_staging", _Staging())   # survives the per-call predictor
             return letterbox_batch_cuda(im, self.imgsz, auto=same_shapes and self.model.pt, stride=self.model.stride,
-                                        device=self.device, staging=self._lb_staging)
+                                        device=self.device, staging=stg)
         arr = np.stack(self.pre_transform(im))
         arr = np.ascontiguousarray(arr[..., ::-1].transpose((0, 3, 1, 2)))
         t = torch.from_numpy(arr).to(self.device, non_blocking=True).float()
@@ -114,40 +113,64 @@ class DetectionPredictor:
         B = im_host.shape[0]
         cb = B // n_chunks
         key = (tuple(im_host.shape), a.max_det)
-        st = getattr(self, "_pipe_state", None)
+        # the staging state lives on the backend: YOLOLite.predict builds a fresh predictor per call, but the pinned
+        # upload pipeline (two device staging batches, streams, events) must survive across calls
+        st = self.model.__dict__.get("_yl_pipe_state")
         if st is None or st["key"] != key:
-            st = {"key": key, "buf": torch.empty(im_host.shape, dtype=torch.float32, device=dev),
+            st = {"key": key, "bufs": [torch.empty(im_host.shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                  "free": [None, None], "turn": 0,
                   "dets": torch.empty((B, a.max_det, 6), dtype=torch.float32, device=dev),
                   "counts": torch.empty((B,), dtype=torch.int32, device=dev),
                   "copy": torch.cuda.Stream(device=dev),
                   "lanes": [torch.cuda.Stream(device=dev) for _ in range(2)],
+                  "post": torch.cuda.Stream(device=dev), "snap": None,
                   "events": [torch.cuda.Event() for _ in range(n_chunks)]}
-            self._pipe_state = st
-        main = torch.cuda.current_stream(dev)
-        st["copy"].wait_stream(main)              # the previous batch's kernels have finished reading `buf`
+            self.model.__dict__["_yl_pipe_state"] = st
+        j = st["turn"]
+        st["turn"] ^= 1
+        buf = st["bufs"][j]
+        # Nothing of this pipeline runs on the caller's stream: upload on the copy stream, chunks alternate between
+        # two lane streams, box rescale + result snapshot on the post stream.  The caller's stream is made to wait
+        # for a batch only when somebody looks at its Results (BatchDetections.ready), so reading batch k-1 never
+        # queues behind the upload / kernels of batch k.
+        # The upload may start as soon as the kernels of the call that last read THIS staging batch are done (two
+        # calls ago): it overlaps the previous call's kernels and the caller's host-side work.
+        if st["free"][j] is not None:
+            st["copy"].wait_event(st["free"][j])
         with torch.cuda.stream(st["copy"]):
             for k in range(n_chunks):
-                st["buf"][k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
+                buf[k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
                 st["events"][k].record(st["copy"])
         model = self.model.model
-        fly = max(1, min(int(self.in_flight), n_chunks))
-        lanes = st["lanes"][:fly] if fly > 1 else [main]
+        fly = max(1, min(int(self.in_flight), n_chunks, 2))
+        lanes = st["lanes"][:fly]
         for ln in lanes:
-            if ln is not main:
-                ln.wait_stream(main)
+            if st.get("snap") is not None:
+                ln.wait_event(st["snap"])        # the previous call's snapshot of dets / counts has been taken
         for k in range(n_chunks):
             ln = lanes[k % fly]
             with torch.cuda.stream(ln):
                 ln.wait_event(st["events"][k])
-                y, _ = model.infer(st["buf"][k * cb:(k + 1) * cb], slot=k % fly)
+                y, _ = model.infer(buf[k * cb:(k + 1) * cb], slot=k % fly)
                 ops.nms_padded(y, a.conf, a.iou, a.classes, a.agnostic_nms, False, a.max_det,
                                out=st["dets"][k * cb:(k + 1) * cb], counts=st["counts"][k * cb:(k + 1) * cb])
+        post = st["post"]
         for ln in lanes:
-            if ln is not main:
-                main.wait_stream(ln)
-        return st["buf"], st["dets"], st["counts"]
+            post.wait_stream(ln)
+        st["free"][j] = torch.cuda.Event()
+        st["free"][j].record(post)
+        return buf, st["dets"], st["counts"], post
 
-    def postprocess(self, preds, img, orig_imgs, nms_out=None):
+    def postprocess(self, preds, img, orig_imgs, nms_out=None, stream=None):
+        """`stream`: run the rescale + snapshot there (the asynchronous host-tensor pipeline) instead of on the
+        caller's current stream."""
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                results = self.postprocess(preds, img, orig_imgs, nms_out=nms_out)
+            st = self.model.__dict__.get("_yl_pipe_state")
+            if st is not None:
+                st["snap"] = results[0]._lazy[0].ready if results and results[0]._lazy else None
+            return results
         a = self.args
         if nms_out is None:
             dets, counts = ops.nms_padded(preds, a.conf, a.iou, a.classes, a.agnostic_nms, False, a.max_det)
@@ -156,20 +179,30 @@ class DetectionPredictor:
         B = dets.shape[0]
         tensor_src = isinstance(orig_imgs, torch.Tensor)
         shapes = [tuple(orig_imgs.shape[2:])] * B if tensor_src else [im.shape[:2] for im in orig_imgs]
-        params = np.empty((B, 5), np.float32)
-        for i, s0 in enumerate(shapes):
-            gain, pad = ops.letterbox_params(tuple(img.shape[2:]), s0)
-            params[i] = (gain, pad[0], pad[1], s0[1], s0[0])
-        pd = torch.from_numpy(params).to(dets.device, non_blocking=True)
+        # per-image (gain, padx, pady, w0, h0) of scale_boxes: cached on the backend per geometry, so a steady stream
+        # of same-shaped batches uploads nothing here
+        cache = self.model.__dict__.setdefault("_yl_scale_params", {})
+        ckey = (tuple(img.shape[2:]), tuple(shapes), str(dets.device))
+        pd = cache.get(ckey)
+        if pd is None:
+            params = np.empty((B, 5), np.float32)
+            for i, s0 in enumerate(shapes):
+                gain, pad = ops.letterbox_params(tuple(img.shape[2:]), s0)
+                params[i] = (gain, pad[0], pad[1], s0[1], s0[0])
+            pd = torch.from_numpy(params).to(dets.device)
+            if len(cache) > 64:
+                cache.clear()
+            cache[ckey] = pd
         _C.check(_C.load().yl_scale_boxes(dets.data_ptr(), counts.data_ptr(), B, dets.shape[1], pd.data_ptr(),
                                           _C.stream_ptr()), "yl_scale_boxes")
-        n = counts.tolist()  # single host sync
-        dets = dets.clone()  # results must not alias the NMS output buffer of the next batch
+        # results must not alias the NMS output buffers of the next batch; the per-image counts are read from the
+        # device when somebody first looks at a result (ONE host sync per batch), so this call never blocks
+        batch = BatchDetections(dets.clone(), counts.clone())
+        batch.ready.record()     # on the stream this runs on; consumers wait for it on THEIR stream
         results = []
         for i in range(B):
             orig = _LazyTensorImage(orig_imgs, i) if tensor_src else orig_imgs[i]
-            r = Results(orig, path=self.batch[0][i], names=self.model.names, boxes=dets[i, : n[i]])
-            results.append(r)
+            results.append(Results(orig, path=self.batch[0][i], names=self.model.names, lazy=(batch, i)))
         return results
 
     # ------------------------------------------------------------------ driver
@@ -194,17 +227,20 @@ class DetectionPredictor:
         with self._lock:
             self.setup_source(source if source is not None else self.args.source)
             self.seen, self.batch = 0, None
-            profilers = tuple(ops.Profile(device=self.device) for _ in range(3))
+            # the reference's Profile synchronises the device on both edges of every stage (ops.py:18-63); that
+            # would serialise upload, kernels and host work, so stage times here are HOST (enqueue) times unless
+            # `verbose` asks for the per-image log, which needs device-accurate numbers
+            profilers = tuple(ops.Profile(device=self.device if self.args.verbose else None) for _ in range(3))
             for self.batch in self.dataset:
                 paths, im0s, s = self.batch
                 n_chunks = self._chunking(im0s)
                 if n_chunks > 1:
                     # host tensor batch: copy / model / NMS run chunk-pipelined (preprocess+inference timed together)
                     with profilers[1]:
-                        im, dets, counts = self._pipelined(im0s, n_chunks)
+                        im, dets, counts, post = self._pipelined(im0s, n_chunks)
                     profilers[0].dt = 0.0
                     with profilers[2]:
-                        self.results = self.postprocess(None, im, im0s, nms_out=(dets, counts))
+                        self.results = self.postprocess(None, im, im0s, nms_out=(dets, counts), stream=post)
                 else:
                     with profilers[0]:
                         im = self.preprocess(im0s)

@@ -82,16 +82,52 @@ class Boxes(BaseTensor):
         return xywh
 
 
+class BatchDetections:
+    """Device-resident NMS output of one batch, (B, max_det, 6) + counts (B,): the per-image row counts are read
+    from the device on first use (ONE host synchronisation per batch), so `predict()` itself never blocks and
+    the next batch's upload overlaps this batch's kernels."""
+
+    def __init__(self, dets: torch.Tensor, counts: torch.Tensor):
+        self.dets, self.counts, self._n = dets, counts, None
+        self.ready = torch.cuda.Event()      # recorded by the producer once dets / counts are final
+
+    def n(self):
+        if self._n is None:
+            cur = torch.cuda.current_stream(self.dets.device)
+            cur.wait_event(self.ready)       # stream-level wait: only THIS batch's work, not whatever was enqueued later
+            self.dets.record_stream(cur)
+            self.counts.record_stream(cur)
+            self._n = self.counts.tolist()
+        return self._n
+
+    def boxes(self, i: int) -> torch.Tensor:
+        return self.dets[i, : self.n()[i]]
+
+
 class Results:
-    def __init__(self, orig_img, path, names, boxes=None, speed=None):
+    def __init__(self, orig_img, path, names, boxes=None, speed=None, lazy=None):
+        """`lazy` = (BatchDetections, image index): `.boxes` materialises on first access."""
         self.orig_img = orig_img
         self.orig_shape = orig_img.shape[:2] if orig_img is not None else None
-        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
+        self._boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
+        self._lazy = lazy
         self.masks = self.probs = self.keypoints = self.obb = None
         self.speed = speed or {"preprocess": None, "inference": None, "postprocess": None}
         self.names = names
         self.path = path
         self.save_dir = None
+
+    @property
+    def boxes(self):
+        if self._boxes is None and self._lazy is not None:
+            batch, i = self._lazy
+            self._boxes = Boxes(batch.boxes(i), self.orig_shape)
+            self._lazy = None
+        return self._boxes
+
+    @boxes.setter
+    def boxes(self, value):
+        self._boxes, self._lazy = value, None
 
     def __len__(self):
         return len(self.boxes) if self.boxes is not None else 0

@@ -59,8 +59,38 @@ class C2f(YLModule):
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=((3, 3), (3, 3)), e=1.0) for _ in range(n))
 
+    #: run [Bottleneck + cv2] as ONE kernel when the block is thin enough (c in {16, 32}); YL_C3K2_FUSE=0 disables
+    fuse_tail = True
+
+    def _tail_fusable(self, out):
+        import os
+
+        from ... import _C, _plan
+        from ._emit import act_flag
+
+        if not self.fuse_tail or os.environ.get("YL_C3K2_FUSE", "1") == "0" or len(self.m) != 1:
+            return False
+        b = self.m[0]
+        if type(b) is not Bottleneck or isinstance(out, _plan.DualDest):
+            return False
+        convs = (b.cv1, b.cv2, self.cv2)
+        if any(type(cv) is not Conv or not hasattr(cv, "bn") or not act_flag(cv.act) or cv.conv.groups != 1
+               or cv.conv.stride != (1, 1) for cv in convs):
+            return False
+        if b.cv1.conv.kernel_size != (3, 3) or b.cv2.conv.kernel_size != (3, 3) or self.cv2.conv.kernel_size != (1, 1):
+            return False
+        c = self.c
+        if b.cv1.conv.in_channels != c or b.cv1.conv.out_channels != c // 2 or b.cv2.conv.out_channels != c:
+            return False
+        return bool(_C.load().yl_c3k2_tail_supported(c, self.cv2.conv.out_channels))
+
     def _emit(self, g, x, out=None):
         c, n = self.c, len(self.m)
+        if self._tail_fusable(out):
+            t = self.cv1._emit(g, x)                 # [y0 | y1]: the only intermediate that touches HBM
+            b = self.m[0]
+            return g.c3k2_tail(t, packed(b.cv1.conv, b.cv1.bn, b.cv1), packed(b.cv2.conv, b.cv2.bn, b.cv2),
+                               packed(self.cv2.conv, self.cv2.bn, self.cv2), b.add, out=out)
         cat = g.alloc(x.n, x.h, x.w, (2 + n) * c)
         self.cv1._emit(g, x, out=cat.slice(0, 2 * c))
         prev = cat.slice(c, c)
