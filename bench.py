@@ -166,6 +166,14 @@ def peaks():
 # ------------------------------------------------------------------------------------------------ main
 def main():
     a = parse()
+    # the contract is ONE JSON line on stdout: park the real stdout and send everything else that writes to fd 1
+    # (NCCL's version banner, library chatter) to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -200,7 +208,7 @@ def main():
                              "sample": f"oracle port (yolo11_ref fp32 unfused + nms_ref), {sample_b}-image steps x{steps}"},
             "e2e": {"value": round(v, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ---------------------------------------------------------------- ours
@@ -421,7 +429,7 @@ def main():
             "launches_per_step": launches_per_step, "detections_last_step": n_det,
             "roofline": roof, "preprocess": prep, "cpu_baseline": cpu_b, "kernel_breakdown": breakdown,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
