@@ -188,6 +188,15 @@ int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream);
  * {gain, padx, pady, w0, h0}. */
 int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream);
 
+/* ---- fused stem --------------------------------------------------------------------------------------------- */
+/* Image ingest + layer 0 + layer 1 (cfg/yolo11.yaml:17-18: Conv(3,c0,3,2) -> Conv(c0,c1,3,2), each conv+BN+SiLU,
+ * nn/modules/conv.py:47-49) in one kernel: reads the caller's NCHW fp32 batch once, keeps the layer-0 map in
+ * shared memory (bf16, same rounding as the unfused path) and writes only the layer-1 output y (n, h/4, w/4, c1).
+ * w0 / w1: yl_fold_bn_pack outputs.  yl_stem_fused_supported(ci, c0, c1): built for ci <= 3, c0 = 16, c1 = 32. */
+int yl_stem_fused_supported(int ci, int c0, int c1);
+int yl_stem_fused(const float* x_nchw, int n, int ci, int h, int w, const void* w0, int ci_pad0, const float* b0, int act0,
+                  const void* w1, int ci_pad1, const float* b1, int act1, const yl_tensor* y, void* stream);
+
 /* ---- fused C3k2 tail ----------------------------------------------------------------------------------------- */
 /* Everything after cv1 of a C3k2 / C2f block with ONE plain Bottleneck (nn/modules/block.py:231-235, 330-343,
  * 720-728): t = cv1(x) = [y0 | y1] (2c channels) ->

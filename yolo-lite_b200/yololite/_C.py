@@ -125,6 +125,9 @@ _PROTOTYPES = {
                                C.c_void_p, C.c_void_p]),
     "yl_xywh2xyxy_inplace": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "yl_scale_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "yl_stem_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "yl_stem_fused": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(Tensor), C.c_void_p]),
     "yl_c3k2_tail_supported": (C.c_int, [C.c_int, C.c_int]),
     "yl_c3k2_tail": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -202,6 +202,21 @@ class Builder:
                    reads=(x, res), writes=(y if store else None, y_up))
         return y if store else None
 
+    def stem_fused(self, x: NchwInput, pc0: PackedConv, pc1: PackedConv, act0: bool, act1: bool, out=None) -> View:
+        """Image ingest + the first two stride-2 3x3 convs in one launch (see yl_stem_fused)."""
+        assert x.view is None and not self.calls, "the fused stem must be the first launch of the plan"
+        h0, w0 = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+        h1, w1 = (h0 - 1) // 2 + 1, (w0 - 1) // 2 + 1
+        y = self._out(out, x.n, h1, w1, pc1.co)
+        yt = y.ct()
+        self._push(self.lib.yl_stem_fused, x.static.data_ptr(), x.n, x.c, x.h, x.w, pc0.w.data_ptr(), pc0.ci_pad,
+                   pc0.bias.data_ptr(), int(act0), pc1.w.data_ptr(), pc1.ci_pad, pc1.bias.data_ptr(), int(act1),
+                   C.byref(yt), keep=(yt, pc0, pc1, x.static), kind="stem_fused",
+                   bytes_=x.n * x.c * x.h * x.w * 4 + x.n * h1 * w1 * pc1.co * 2,
+                   flops=2 * x.n * (h0 * w0 * pc0.co * x.c * 9 + h1 * w1 * pc1.co * pc0.co * 9),
+                   desc=f"[{x.c}->{pc0.co} k3s2, {pc0.co}->{pc1.co} k3s2] {x.h}x{x.w} nchw-f32 in", writes=(y,))
+        return y
+
     def c3k2_tail(self, t: View, pa: PackedConv, pb: PackedConv, p2: PackedConv, shortcut: bool, out=None) -> View:
         """Fused [Bottleneck(3x3, 3x3) + C2f.cv2] on t = cv1(x) = [y0 | y1] (see yl_c3k2_tail)."""
         y = self._out(out, t.n, t.h, t.w, p2.co)
@@ -295,7 +310,7 @@ class Plan:
         if self.graph is not None or ingest_ptr is not None:
             for fn, args, _ in self.calls[: self._skip if self.graph is not None else 1]:
                 a = (ingest_ptr,) + tuple(args[1:]) if (ingest_ptr is not None and
-                                                         fn.__name__ in ("yl_nchw_to_nhwc", "yl_stem_conv")) else args
+                                                         fn.__name__ in ("yl_nchw_to_nhwc", "yl_stem_conv", "yl_stem_fused")) else args
                 _C.check(fn(*a, s), fn.__name__)
             first = self._skip if self.graph is not None else 1
         if self.graph is not None:

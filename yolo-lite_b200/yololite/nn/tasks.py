@@ -134,6 +134,16 @@ def initialize_weights(model: nn.Module):
             m.inplace = True
 
 
+def fused_up_guard(layers):
+    """Indices of layers whose output feeds an nn.Upsample (those producers need the dual-destination conv)."""
+    out = set()
+    for u, m in enumerate(layers):
+        if isinstance(m, nn.Upsample):
+            f = m.f if isinstance(m.f, int) else m.f[0]
+            out.add(u - 1 if f == -1 else f)
+    return out
+
+
 class BaseModel(YLModule):
     """Layer-list model executed through a cached static plan (one per input shape and device)."""
 
@@ -239,8 +249,19 @@ class BaseModel(YLModule):
                     fused_up[j] = u
         done_up = {}
 
+        # layers 0 + 1 as one launch (image ingest + two stride-2 3x3 convs) when layer 0 feeds only layer 1
+        fuse_stem = self._stem_fusable(g, x, layers, srcs, n_uses)
         cur = x
         for i, m in enumerate(layers):
+            if fuse_stem and i == 0:
+                continue
+            if fuse_stem and i == 1:
+                from .modules._emit import act_flag, packed
+
+                l0, l1 = layers[0], layers[1]
+                cur = ys[1] = g.stem_fused(x, packed(l0.conv, l0.bn, l0), packed(l1.conv, l1.bn, l1), act_flag(l0.act),
+                                           act_flag(l1.act), out=dest_for(1))
+                continue
             inp = [ys[j] if j >= 0 else x for j in srcs[i]]
             if isinstance(m, Detect):
                 return m._emit(g, inp)
@@ -262,6 +283,29 @@ class BaseModel(YLModule):
                 cur = emit_any(g, m, inp[0], out=dest_for(i))
             ys[i] = cur
         return cur
+
+    #: run layers 0 and 1 as one kernel when the shapes allow (YL_STEM_FUSE=0 disables)
+    fuse_stem = True
+
+    def _stem_fusable(self, g, x, layers, srcs, n_uses):
+        import os
+
+        from .. import _C
+
+        if not self.fuse_stem or os.environ.get("YL_STEM_FUSE", "1") == "0" or len(layers) < 3:
+            return False
+        if not isinstance(x, _plan.NchwInput) or x.view is not None or g.calls:
+            return False
+        l0, l1 = layers[0], layers[1]
+        if type(l0) is not Conv or type(l1) is not Conv or srcs[1] != [0] or n_uses[0] != 1 or 1 in fused_up_guard(layers):
+            return False
+        for cv in (l0, l1):
+            c = cv.conv
+            if c.kernel_size != (3, 3) or c.stride != (2, 2) or c.groups != 1 or not hasattr(cv, "bn") or c.bias is not None:
+                return False
+        if l0.conv.in_channels != x.c:
+            return False
+        return bool(_C.load().yl_stem_fused_supported(x.c, l0.conv.out_channels, l1.conv.out_channels))
 
     @staticmethod
     def _out_channels(layers, k, memo):
