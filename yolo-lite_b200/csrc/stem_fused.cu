@@ -61,7 +61,8 @@ constexpr int SF_OFF_IN = 0;                                      // uint2 [35][
 constexpr int SF_OFF_L0 = SF_OFF_IN + SF_RI * SF_CI * 8;           // 2 planes x [17][17] x 48 B
 constexpr int SF_OFF_W1 = SF_OFF_L0 + 2 * SF_R0 * SF_EC * SF_P0;
 constexpr int SF_OFF_B = SF_OFF_W1 + 32 * SF_W1S;                  // b0[16], b1[32] fp32
-constexpr int SF_SMEM = SF_OFF_B + 48 * 4;
+constexpr int SF_OFF_TAB = SF_OFF_B + 48 * 4;                      // uint2 [36 m-tiles][16 rows]: stage-1 geometry
+constexpr int SF_SMEM = SF_OFF_TAB + SF_M0 * 16 * 8;
 
 __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParams p) {
     extern __shared__ __align__(16) uint8_t sf_smem[];
@@ -104,18 +105,28 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
                 bw0[ks][nt][hh] = v;
             }
     }
-    // smem word offsets of this thread's k slots relative to the patch pixel of its output pixel (stage 1 A operand)
+    // smem word offsets of this thread's k slots relative to the patch pixel of its output pixel (stage 1 A operand);
+    // slots beyond tap 8 meet zero B fragments, so they may read any valid word
     int woff[3][2];
-    bool kval[3][2];
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const int k = 16 * ks + 2 * t + hh * 8;
             const int tap = k >> 2, r = tap / 3, s2 = tap - 3 * r;
-            kval[ks][hh] = tap < 9;
-            woff[ks][hh] = kval[ks][hh] ? ((r * SF_CI + s2) * 2 + ((k >> 1) & 1)) : 0;
+            woff[ks][hh] = tap < 9 ? ((r * SF_CI + s2) * 2 + ((k >> 1) & 1)) : 0;
         }
+    // stage-1 geometry is the same for every tile: per (m-tile, row) the input-patch word offset of the pixel, its
+    // destination in the parity-split layer-0 patch and its (row, col) for the border mask
+    uint2* s_tab = reinterpret_cast<uint2*>(sf_smem + SF_OFF_TAB);
+    for (int i = threadIdx.x; i < SF_M0 * 16; i += blockDim.x) {
+        const bool valid = i < SF_R0 * SF_C0;
+        const int idx = valid ? i : SF_R0 * SF_C0 - 1;
+        const int er = idx / SF_C0, ec = idx - er * SF_C0;
+        const uint32_t aoff = (uint32_t)(((2 * er) * SF_CI + 2 * ec + 1) * 2);
+        const uint32_t doff = (uint32_t)((((ec & 1) * SF_R0 + er) * SF_EC + (ec >> 1)) * SF_P0);
+        s_tab[i] = make_uint2(aoff | ((uint32_t)(valid ? er : 255) << 16) | ((uint32_t)ec << 24), doff);
+    }
     griddep_wait();
 
     const long long plane = (long long)p.H * p.W;
@@ -131,37 +142,55 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
         {
             const float* xn = p.x + (long long)n * p.CI * plane;
             constexpr int QUADS = SF_CI / 4;
-            for (int item = threadIdx.x; item < SF_RI * QUADS; item += blockDim.x) {
-                const int pr = item / QUADS, q = item - pr * QUADS;
-                const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
-                float v[4][4];
+            constexpr int ITEMS = SF_RI * QUADS;                       // 630 quads of 4 pixels
+            constexpr int ROUNDS = (ITEMS + 255) / 256;
+            if (vec_ok) {
+                // quads are 16-byte aligned in the image, so each one is entirely inside or entirely outside: every
+                // load of the patch is issued before the first conversion (one HBM round trip per tile, not three)
+                float4 f[ROUNDS][3];
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci)
+                for (int j = 0; j < ROUNDS; ++j) {
+                    const int item = threadIdx.x + j * 256;
+                    const int pr = item / QUADS, q = item - pr * QUADS;
+                    const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
+                    const bool ok = item < ITEMS && hi >= 0 && hi < p.H && wi0 >= 0 && wi0 < p.W;
+                    const float* src0 = xn + (long long)(ok ? hi : 0) * p.W + (ok ? wi0 : 0);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[ci][e] = 0.f;
-                if (hi >= 0 && hi < p.H) {
-                    const float* src0 = xn + (long long)hi * p.W + wi0;
-                    if (vec_ok && wi0 >= 0 && wi0 + 3 < p.W) {
-#pragma unroll
-                        for (int ci = 0; ci < 3; ++ci)
-                            if (ci < p.CI) {
-                                const float4 f = __ldg(reinterpret_cast<const float4*>(src0 + ci * plane));
-                                v[ci][0] = f.x; v[ci][1] = f.y; v[ci][2] = f.z; v[ci][3] = f.w;
-                            }
-                    } else {
-#pragma unroll
-                        for (int ci = 0; ci < 3; ++ci)
-                            if (ci < p.CI)
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (wi0 + e >= 0 && wi0 + e < p.W) v[ci][e] = __ldg(src0 + ci * plane + e);
+                    for (int ci = 0; ci < 3; ++ci) {
+                        f[j][ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok && ci < p.CI) f[j][ci] = __ldg(reinterpret_cast<const float4*>(src0 + ci * plane));
                     }
                 }
-                uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
-                dst[0] = make_uint4(pack_bf16x2(v[0][0], v[1][0]), pack_bf16x2(v[2][0], v[3][0]),
-                                    pack_bf16x2(v[0][1], v[1][1]), pack_bf16x2(v[2][1], v[3][1]));
-                dst[1] = make_uint4(pack_bf16x2(v[0][2], v[1][2]), pack_bf16x2(v[2][2], v[3][2]),
-                                    pack_bf16x2(v[0][3], v[1][3]), pack_bf16x2(v[2][3], v[3][3]));
+#pragma unroll
+                for (int j = 0; j < ROUNDS; ++j) {
+                    const int item = threadIdx.x + j * 256;
+                    if (item >= ITEMS) continue;
+                    const int pr = item / QUADS, q = item - pr * QUADS;
+                    uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
+                    dst[0] = make_uint4(pack_bf16x2(f[j][0].x, f[j][1].x), pack_bf16x2(f[j][2].x, 0.f),
+                                        pack_bf16x2(f[j][0].y, f[j][1].y), pack_bf16x2(f[j][2].y, 0.f));
+                    dst[1] = make_uint4(pack_bf16x2(f[j][0].z, f[j][1].z), pack_bf16x2(f[j][2].z, 0.f),
+                                        pack_bf16x2(f[j][0].w, f[j][1].w), pack_bf16x2(f[j][2].w, 0.f));
+                }
+            } else {
+                for (int item = threadIdx.x; item < ITEMS; item += blockDim.x) {
+                    const int pr = item / QUADS, q = item - pr * QUADS;
+                    const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
+                    float v[3][4];
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[ci][e] = 0.f;
+                            if (ci < p.CI && hi >= 0 && hi < p.H && wi0 + e >= 0 && wi0 + e < p.W)
+                                v[ci][e] = __ldg(xn + ci * plane + (long long)hi * p.W + wi0 + e);
+                        }
+                    uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
+                    dst[0] = make_uint4(pack_bf16x2(v[0][0], v[1][0]), pack_bf16x2(v[2][0], 0.f),
+                                        pack_bf16x2(v[0][1], v[1][1]), pack_bf16x2(v[2][1], 0.f));
+                    dst[1] = make_uint4(pack_bf16x2(v[0][2], v[1][2]), pack_bf16x2(v[2][2], 0.f),
+                                        pack_bf16x2(v[0][3], v[1][3]), pack_bf16x2(v[2][3], 0.f));
+                }
             }
         }
         __syncthreads();
@@ -169,20 +198,20 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
         // ================= stage 1: layer 0 on the 17 x 33 halo region =================
         {
             const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_in);
+            // border mask of the layer-0 map in patch coordinates (uniform per tile)
+            const int er_lo = oh0 == 0 ? 1 : 0, er_hi = min(SF_R0, p.H0 - (2 * oh0 - 1));
+            const int ec_lo = ow0 == 0 ? 1 : 0, ec_hi = min(SF_C0, p.W0 - (2 * ow0 - 1));
             for (int mt = warp; mt < SF_M0; mt += 8) {
                 uint32_t a[3][4];
-                int er[2], ec[2];
+                uint2 te[2];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    int idx = mt * 16 + g + half * 8;
-                    idx = idx < SF_R0 * SF_C0 ? idx : SF_R0 * SF_C0 - 1;
-                    er[half] = idx / SF_C0;
-                    ec[half] = idx - er[half] * SF_C0;
-                    const uint32_t* px = pw + ((2 * er[half]) * SF_CI + 2 * ec[half] + 1) * 2;
+                    te[half] = s_tab[mt * 16 + g + half * 8];
+                    const uint32_t* px = pw + (te[half].x & 0xffffu);
 #pragma unroll
                     for (int ks = 0; ks < 3; ++ks) {
-                        a[ks][half] = kval[ks][0] ? px[woff[ks][0]] : 0u;
-                        a[ks][2 + half] = kval[ks][1] ? px[woff[ks][1]] : 0u;
+                        a[ks][half] = px[woff[ks][0]];
+                        a[ks][2 + half] = px[woff[ks][1]];
                     }
                 }
                 float acc[2][4];
@@ -195,11 +224,10 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
                 }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    if (mt * 16 + g + half * 8 >= SF_R0 * SF_C0) continue;
-                    const int h0i = 2 * oh0 - 1 + er[half], w0i = 2 * ow0 - 1 + ec[half];   // layer-0 map coordinates
-                    const bool in = h0i >= 0 && h0i < p.H0 && w0i >= 0 && w0i < p.W0;
-                    // parity plane (even / odd patch column), then [row][col / 2]
-                    const uint32_t dst = sL0 + (uint32_t)((((ec[half] & 1) * SF_R0 + er[half]) * SF_EC + (ec[half] >> 1)) * SF_P0);
+                    const int er = (int)((te[half].x >> 16) & 0xffu), ec = (int)(te[half].x >> 24);
+                    if (er == 255) continue;                       // row beyond the 17 x 33 region
+                    const bool in = er >= er_lo && er < er_hi && ec >= ec_lo && ec < ec_hi;
+                    const uint32_t dst = sL0 + te[half].y + (uint32_t)(4 * t);
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
                         float v0 = acc[nt][half * 2], v1 = acc[nt][half * 2 + 1];
@@ -207,8 +235,7 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
                             v0 = silu_fast(v0);
                             v1 = silu_fast(v1);
                         }
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)((nt * 8 + 2 * t) * 2)),
-                                     "r"(in ? pack_bf16x2(v0, v1) : 0u)
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)(nt * 16)), "r"(in ? pack_bf16x2(v0, v1) : 0u)
                                      : "memory");
                     }
                 }
