@@ -395,6 +395,7 @@ def main():
                 "frac": round(ach / hbm, 4), "traffic": ncu_traffic(top, model_name, a.batch),
                 "algorithmic_bytes_per_launch": round(tk["bytes"] / tk["launches"], 1),
                 "peak_source": f"MEASURED_PEAKS.json ({src})",
+                "timing": "CUDA events around 4 back-to-back launches of every plan launch (eager pass in plan order), /4",
                 "launches_per_step": tk["launches"], "avg_launch_us": round(tk["ms"] * 1e3 / tk["launches"], 2),
                 "tensor_tflops": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3), 1), "tensor_peak_tflops": tf,
                 "tensor_frac": round(tk["flops"] / 1e12 / (tk["ms"] / 1e3) / tf, 4)}

@@ -131,69 +131,89 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
 
     const long long plane = (long long)p.H * p.W;
     const bool vec_ok = (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    constexpr int QUADS = SF_CI / 4;
+    constexpr int ITEMS = SF_RI * QUADS;                       // 630 quads of 4 pixels
+    constexpr int ROUNDS = (ITEMS + 255) / 256;
+    float4 pf[ROUNDS][3];                                      // the next tile's patch, in flight across stage 2
+
+    // Stage 0 is split in two so that its HBM round trip hides behind stage 2 of the previous tile: `patch_issue`
+    // only issues the loads (quads are 16-byte aligned in the image, so with W % 4 == 0 each one is entirely inside
+    // or entirely outside), `patch_store` rounds to bf16 and writes [row][col][4 ch].
+    auto patch_issue = [&](int tile) {
+        const int ow0 = (tile % p.tiles_w) * SF_TW;
+        const int oh0 = ((tile / p.tiles_w) % p.tiles_h) * SF_TH;
+        const int n = tile / (p.tiles_w * p.tiles_h);
+        const int ir0 = 4 * oh0 - 3, ic0 = 4 * ow0 - 4;   // input coords of patch (0, 0)
+        const float* xn = p.x + (long long)n * p.CI * plane;
+#pragma unroll
+        for (int j = 0; j < ROUNDS; ++j) {
+            const int item = threadIdx.x + j * 256;
+            const int pr = item / QUADS, q = item - pr * QUADS;
+            const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
+            const bool ok = item < ITEMS && hi >= 0 && hi < p.H && wi0 >= 0 && wi0 < p.W;
+            const float* src0 = xn + (long long)(ok ? hi : 0) * p.W + (ok ? wi0 : 0);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                pf[j][ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && ci < p.CI) pf[j][ci] = __ldg(reinterpret_cast<const float4*>(src0 + ci * plane));
+            }
+        }
+    };
+    auto patch_store = [&]() {
+#pragma unroll
+        for (int j = 0; j < ROUNDS; ++j) {
+            const int item = threadIdx.x + j * 256;
+            if (item >= ITEMS) continue;
+            const int pr = item / QUADS, q = item - pr * QUADS;
+            uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
+            dst[0] = make_uint4(pack_bf16x2(pf[j][0].x, pf[j][1].x), pack_bf16x2(pf[j][2].x, 0.f),
+                                pack_bf16x2(pf[j][0].y, pf[j][1].y), pack_bf16x2(pf[j][2].y, 0.f));
+            dst[1] = make_uint4(pack_bf16x2(pf[j][0].z, pf[j][1].z), pack_bf16x2(pf[j][2].z, 0.f),
+                                pack_bf16x2(pf[j][0].w, pf[j][1].w), pack_bf16x2(pf[j][2].w, 0.f));
+        }
+    };
+    // general shapes (W % 4 != 0 or an unaligned base): element-wise, synchronous
+    auto patch_slow = [&](int tile) {
+        const int ow0 = (tile % p.tiles_w) * SF_TW;
+        const int oh0 = ((tile / p.tiles_w) % p.tiles_h) * SF_TH;
+        const int n = tile / (p.tiles_w * p.tiles_h);
+        const int ir0 = 4 * oh0 - 3, ic0 = 4 * ow0 - 4;
+        const float* xn = p.x + (long long)n * p.CI * plane;
+        for (int item = threadIdx.x; item < ITEMS; item += blockDim.x) {
+            const int pr = item / QUADS, q = item - pr * QUADS;
+            const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
+            float v[3][4];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[ci][e] = 0.f;
+                    if (ci < p.CI && hi >= 0 && hi < p.H && wi0 + e >= 0 && wi0 + e < p.W)
+                        v[ci][e] = __ldg(xn + ci * plane + (long long)hi * p.W + wi0 + e);
+                }
+            uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
+            dst[0] = make_uint4(pack_bf16x2(v[0][0], v[1][0]), pack_bf16x2(v[2][0], 0.f), pack_bf16x2(v[0][1], v[1][1]),
+                                pack_bf16x2(v[2][1], 0.f));
+            dst[1] = make_uint4(pack_bf16x2(v[0][2], v[1][2]), pack_bf16x2(v[2][2], 0.f), pack_bf16x2(v[0][3], v[1][3]),
+                                pack_bf16x2(v[2][3], 0.f));
+        }
+    };
+
+    if ((int)blockIdx.x < p.total_tiles) {
+        if (vec_ok) {
+            patch_issue(blockIdx.x);
+            patch_store();
+        } else {
+            patch_slow(blockIdx.x);
+        }
+    }
+    __syncthreads();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ow0 = (tile % p.tiles_w) * SF_TW;
         const int oh0 = ((tile / p.tiles_w) % p.tiles_h) * SF_TH;
         const int n = tile / (p.tiles_w * p.tiles_h);
-        const int ir0 = 4 * oh0 - 3, ic0 = 4 * ow0 - 4;   // input coords of patch (0, 0); layer-0 pixel (pr, pc) reads
-                                                          // patch rows 2pr + dr and columns 2pc + dc + 1
-
-        // ================= stage 0: input patch -> bf16 [row][col][4 ch] =================
-        {
-            const float* xn = p.x + (long long)n * p.CI * plane;
-            constexpr int QUADS = SF_CI / 4;
-            constexpr int ITEMS = SF_RI * QUADS;                       // 630 quads of 4 pixels
-            constexpr int ROUNDS = (ITEMS + 255) / 256;
-            if (vec_ok) {
-                // quads are 16-byte aligned in the image, so each one is entirely inside or entirely outside: every
-                // load of the patch is issued before the first conversion (one HBM round trip per tile, not three)
-                float4 f[ROUNDS][3];
-#pragma unroll
-                for (int j = 0; j < ROUNDS; ++j) {
-                    const int item = threadIdx.x + j * 256;
-                    const int pr = item / QUADS, q = item - pr * QUADS;
-                    const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
-                    const bool ok = item < ITEMS && hi >= 0 && hi < p.H && wi0 >= 0 && wi0 < p.W;
-                    const float* src0 = xn + (long long)(ok ? hi : 0) * p.W + (ok ? wi0 : 0);
-#pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) {
-                        f[j][ci] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok && ci < p.CI) f[j][ci] = __ldg(reinterpret_cast<const float4*>(src0 + ci * plane));
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < ROUNDS; ++j) {
-                    const int item = threadIdx.x + j * 256;
-                    if (item >= ITEMS) continue;
-                    const int pr = item / QUADS, q = item - pr * QUADS;
-                    uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
-                    dst[0] = make_uint4(pack_bf16x2(f[j][0].x, f[j][1].x), pack_bf16x2(f[j][2].x, 0.f),
-                                        pack_bf16x2(f[j][0].y, f[j][1].y), pack_bf16x2(f[j][2].y, 0.f));
-                    dst[1] = make_uint4(pack_bf16x2(f[j][0].z, f[j][1].z), pack_bf16x2(f[j][2].z, 0.f),
-                                        pack_bf16x2(f[j][0].w, f[j][1].w), pack_bf16x2(f[j][2].w, 0.f));
-                }
-            } else {
-                for (int item = threadIdx.x; item < ITEMS; item += blockDim.x) {
-                    const int pr = item / QUADS, q = item - pr * QUADS;
-                    const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
-                    float v[3][4];
-#pragma unroll
-                    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            v[ci][e] = 0.f;
-                            if (ci < p.CI && hi >= 0 && hi < p.H && wi0 + e >= 0 && wi0 + e < p.W)
-                                v[ci][e] = __ldg(xn + ci * plane + (long long)hi * p.W + wi0 + e);
-                        }
-                    uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
-                    dst[0] = make_uint4(pack_bf16x2(v[0][0], v[1][0]), pack_bf16x2(v[2][0], 0.f),
-                                        pack_bf16x2(v[0][1], v[1][1]), pack_bf16x2(v[2][1], 0.f));
-                    dst[1] = make_uint4(pack_bf16x2(v[0][2], v[1][2]), pack_bf16x2(v[2][2], 0.f),
-                                        pack_bf16x2(v[0][3], v[1][3]), pack_bf16x2(v[2][3], 0.f));
-                }
-            }
-        }
-        __syncthreads();
+        const int next = tile + (int)gridDim.x;
+        // layer-0 pixel (pr, pc) of the halo region reads patch rows 2pr + dr and columns 2pc + dc + 1
 
         // ================= stage 1: layer 0 on the 17 x 33 halo region =================
         {
@@ -242,6 +262,7 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
             }
         }
         __syncthreads();
+        if (vec_ok && next < p.total_tiles) patch_issue(next);   // in flight during stage 2
 
         // ================= stage 2: layer 1, warp = output row =================
         {
@@ -305,7 +326,12 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
                 if (st_ok) *reinterpret_cast<uint4*>(yp + np * 16) = make_uint4(v0, v1, v2, v3);
             }
         }
-        __syncthreads();   // the next tile overwrites both patches
+        // stage 1 of this tile has finished reading the input patch (barrier above): refill it for the next tile
+        if (next < p.total_tiles) {
+            if (vec_ok) patch_store();
+            else patch_slow(next);
+        }
+        __syncthreads();   // next patch complete; every warp is done with this tile's layer-0 patch
     }
 }
 

@@ -326,9 +326,13 @@ class Plan:
             if rc != 0:
                 check(rc, fn.__name__)
 
-    def time_launches(self, reps: int = 3):
+    def time_launches(self, reps: int = 3, inner: int = 4):
         """Per-launch device time (ms, median of `reps` eager passes in plan order) via CUDA events on the
-        launching stream.  Cache state is the real one: each launch runs right after its producers."""
+        launching stream.  Every launch is issued `inner` times back to back between its two events and the
+        elapsed time divided by `inner`: all launches are idempotent (outputs are pure functions of other buffers),
+        so this measures the kernel's steady-state duration and keeps the ~5 us of event/launch latency out of a
+        10 us kernel.  Cache state is the real one for the first of the `inner` launches (it runs right after its
+        producers); tensors larger than L2 stream from HBM every time."""
         n = len(self.calls)
         s = _C.stream_ptr()
         times = []
@@ -336,10 +340,11 @@ class Plan:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
             ev[0].record()
             for i, (fn, args, _) in enumerate(self.calls):
-                _C.check(fn(*args, s), fn.__name__)
+                for _k in range(inner):
+                    _C.check(fn(*args, s), fn.__name__)
                 ev[i + 1].record()
             torch.cuda.synchronize(self.device)
-            times.append([ev[i].elapsed_time(ev[i + 1]) for i in range(n)])
+            times.append([ev[i].elapsed_time(ev[i + 1]) / inner for i in range(n)])
         t = torch.tensor(times).median(0).values.tolist()
         return t
 
