@@ -210,6 +210,16 @@ int yl_c3k2_tail(const yl_tensor* t, const yl_tensor* y, const void* wa, const f
                  const void* wb, const float* bb, int wb_ci_pad, const void* w2, const float* b2, int w2_ci_pad,
                  int shortcut, void* stream);
 
+/* ---- validator metric (the caller after the path) ------------------------------------------------- */
+/* box_iou (utils/metrics.py:51-70) + match_predictions (engine/validator.py:195-233, :410-429) for a whole batch:
+ * dets (B,max_det,6) [x1,y1,x2,y2,conf,cls] + counts (B) as written by yl_nms_batched (already in label space),
+ * gt_boxes (L,4) xyxy + gt_cls (L) fp32 for all images back to back, gt_offsets (B+1) int32 (image b owns labels
+ * [gt_offsets[b], gt_offsets[b+1]), at most max_labels_per_image of them), iou_thresholds_dev (n <= 16, device).
+ * tp (B,max_det,n) uint8: detection d is a true positive at threshold t.  Rows >= counts[b] are zero. */
+int yl_match_predictions(const float* dets, const int32_t* counts, int B, int max_det, const float* gt_boxes,
+                         const float* gt_cls, const int32_t* gt_offsets, int max_labels_per_image,
+                         const float* iou_thresholds_dev, int n_thresholds, uint8_t* tp, void* stream);
+
 /* ---- image preprocess (the step before the path) ---------------------------------------------- */
 /* One source image of a letterbox batch: HWC uint8 BGR on the DEVICE, `pitch` bytes per row; it is resized to
  * (new_w, new_h) with cv2's 8-bit INTER_LINEAR arithmetic (skipped when the size already matches) and placed

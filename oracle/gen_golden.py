@@ -8,6 +8,8 @@ Fixtures (all seeded; weights are the name-keyed values of oracle/weights.py, so
                             PSABlock, C2PSA, Detect, DFL) on small inputs
   nms_torchvision.npz       torchvision.ops.nms (CPU, the arithmetic behind ops.py:265) known-answer cases
   nms_reference.npz         reference ops.non_max_suppression (max_time_img=1e9) on synthetic predictions
+  val_metrics.npz           reference box_iou + DetectionValidator.match_predictions (validator.py:195-233) per image
+                            and utils.metrics.ap_per_class on seeded synthetic detections / labels
   letterbox.npz             reference LetterBox (data/augment.py:612-681) + predictor.preprocess arithmetic
                             (engine/predictor.py:67-85) on seeded uint8 images (only seeds + outputs stored)
 """
@@ -182,6 +184,73 @@ def gen_nms_reference():
     np.savez_compressed(GOLD / "nms_reference.npz", **out)
 
 
+def val_case(seed, B=6, max_det=40, nc=5):
+    """Seeded synthetic validation batch: labels + detections (jittered labels and random boxes), conf-sorted.
+    Coordinates are drawn on a 1/64 grid so IoUs are exact in fp32 but distinct (no ties)."""
+    g = np.random.default_rng(seed)
+    dets = np.zeros((B, max_det, 6), np.float32)
+    counts = np.zeros((B,), np.int32)
+    gtb, gtc, offs = [], [], [0]
+    for b in range(B):
+        L = int(g.integers(0, 12)) if b else 0            # image 0 has no labels
+        xy = g.integers(0, 400 * 64, (L, 2)) / 64.0
+        wh = g.integers(20 * 64, 200 * 64, (L, 2)) / 64.0
+        lab = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        cl = g.integers(0, nc, (L,)).astype(np.float32)
+        n = int(g.integers(0, max_det + 1)) if b != 1 else 0   # image 1 has no detections
+        rows = []
+        for i in range(n):
+            if L and g.random() < 0.7:
+                j = int(g.integers(0, L))
+                jit = g.integers(-30 * 64, 30 * 64, (4,)) / 64.0
+                box = lab[j] + jit.astype(np.float32)
+                c = cl[j] if g.random() < 0.85 else float(g.integers(0, nc))
+            else:
+                p0 = g.integers(0, 400 * 64, (2,)) / 64.0
+                box = np.concatenate([p0, p0 + g.integers(20 * 64, 200 * 64, (2,)) / 64.0]).astype(np.float32)
+                c = float(g.integers(0, nc))
+            rows.append([*box, 0.0, c])
+        rows = np.asarray(rows, np.float32).reshape(-1, 6)
+        rows[:, 4] = np.sort(g.random(n).astype(np.float32))[::-1]
+        dets[b, :n] = rows
+        counts[b] = n
+        gtb.append(lab)
+        gtc.append(cl)
+        offs.append(offs[-1] + L)
+    return dets, counts, np.concatenate(gtb).reshape(-1, 4), np.concatenate(gtc), np.asarray(offs, np.int32)
+
+
+def gen_val_metrics():
+    import_reference()
+    from yololite.engine.validator import DetectionValidator  # noqa: F401  (the reference's class)
+    from yololite.utils.metrics import ap_per_class, box_iou
+
+    iouv = torch.linspace(0.5, 0.95, 10)
+    fake = type("V", (), {"iouv": iouv})()                # match_predictions only reads self.iouv
+    out = {"seeds": np.asarray([11, 12, 13])}
+    for seed in (11, 12, 13):
+        dets, counts, gtb, gtc, offs = val_case(seed)
+        tps = np.zeros((dets.shape[0], dets.shape[1], 10), bool)
+        for b in range(dets.shape[0]):
+            n, s, e = counts[b], offs[b], offs[b + 1]
+            if n == 0 or e == s:
+                continue
+            d = torch.from_numpy(dets[b, :n])
+            iou = box_iou(torch.from_numpy(gtb[s:e]), d[:, :4])
+            tps[b, :n] = DetectionValidator.match_predictions(fake, d[:, 5], torch.from_numpy(gtc[s:e]), iou).numpy()
+        out[f"tp_{seed}"] = tps
+        # ap_per_class on the flattened stats of this case
+        sel = [(b, i) for b in range(dets.shape[0]) for i in range(counts[b])]
+        tp = np.asarray([tps[b, i] for b, i in sel]).reshape(-1, 10)
+        conf = np.asarray([dets[b, i, 4] for b, i in sel])
+        pc = np.asarray([dets[b, i, 5] for b, i in sel])
+        r = ap_per_class(tp, conf, pc, gtc)
+        for k, name in zip(range(7), ("tpn", "fpn", "p", "r", "f1", "ap", "cls")):
+            out[f"{name}_{seed}"] = np.asarray(r[k])
+    np.savez_compressed(GOLD / "val_metrics.npz", **out)
+    print("val_metrics.npz")
+
+
 LETTERBOX_CASES = [
     # (src h, src w, new_shape, auto, scaleup, seed)
     (97, 131, (64, 64), False, True, 1),      # downscale, wide
@@ -226,6 +295,10 @@ if __name__ == "__main__":
     if "--only-letterbox" in sys.argv:
         gen_letterbox()
         sys.exit(0)
+    if "--only-val" in sys.argv:
+        gen_val_metrics()
+        sys.exit(0)
+    gen_val_metrics()
     gen_letterbox()
     gen_nms_torchvision()
     gen_nms_reference()

@@ -14,14 +14,14 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SOURCES = ["runtime.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "layout.cu", "pool.cu", "attention.cu",
-           "decode.cu", "nms.cu", "preprocess.cu", "c3k2_fused.cu", "stem_fused.cu"]
+           "decode.cu", "nms.cu", "preprocess.cu", "c3k2_fused.cu", "stem_fused.cu", "metrics.cu"]
 HEADERS = [HERE / "common.cuh", HERE.parents[1] / "include" / "yl11.h"]
 OUT_DIR = HERE.parent / "yololite" / "lib"
 LIB = OUT_DIR / "libyl11.so"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
 # nms.cu and decode.cu need IEEE arithmetic (bit-exact IoU / accurate expf): no fast-math there
-NO_FAST_MATH = {"nms.cu", "decode.cu", "preprocess.cu"}
+NO_FAST_MATH = {"nms.cu", "decode.cu", "preprocess.cu", "metrics.cu"}
 
 
 def _nvcc():

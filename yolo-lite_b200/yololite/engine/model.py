@@ -70,12 +70,14 @@ class YOLOLite(nn.Module):
             self.predictor = predictor
         return self.predictor(source=source, stream=stream)
 
-    def val(self, **kwargs):
+    def val(self, dataloader=None, **kwargs):
+        """Validate on labelled batches (reference engine/model.py val).  `dataloader`: iterable of batch dicts in
+        the reference's collate layout; building one from a dataset yaml is out of scope (see engine/validator.py)."""
         from .validator import DetectionValidator
 
         custom = {"rect": True}
         args = {**self.overrides, **custom, **kwargs, "mode": "val"}
-        validator = DetectionValidator(args=args)
+        validator = DetectionValidator(dataloader=dataloader, args=args)
         validator(model=self.model)
         self.metrics = validator.metrics
         return validator.metrics
