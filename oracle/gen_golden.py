@@ -10,6 +10,9 @@ Fixtures (all seeded; weights are the name-keyed values of oracle/weights.py, so
   nms_reference.npz         reference ops.non_max_suppression (max_time_img=1e9) on synthetic predictions
   val_metrics.npz           reference box_iou + DetectionValidator.match_predictions (validator.py:195-233) per image
                             and utils.metrics.ap_per_class on seeded synthetic detections / labels
+  ckpt_tiny.pt / ckpt_tiny_out.npz   a checkpoint PICKLED BY THE REFERENCE ({"model": DetectionModel.half(), ...},
+                            engine/trainer.py:360-388 layout) of a narrow yolo11 (width 0.125, nc 16) + the reference's
+                            fp32 CPU output for it: the checkpoint-ingest fixture
   letterbox.npz             reference LetterBox (data/augment.py:612-681) + predictor.preprocess arithmetic
                             (engine/predictor.py:67-85) on seeded uint8 images (only seeds + outputs stored)
 """
@@ -251,6 +254,27 @@ def gen_val_metrics():
     print("val_metrics.npz")
 
 
+def gen_checkpoint():
+    import_reference()
+    from yololite.nn.tasks import DetectionModel, yaml_model_load
+
+    d = yaml_model_load("/root/reference/yololite/cfg/yolo11n.yaml")
+    d["scales"] = {"n": [0.5, 0.125, 1024]}              # narrow: 0.8 M parameters keep the fixture small
+    d["nc"] = 16
+    m = DetectionModel(d, verbose=False).eval()
+    fill_state_dict_(m)
+    ckpt = {"epoch": -1, "best_fitness": None, "model": m.half(), "ema": None, "updates": None, "optimizer": None,
+            "train_args": {"imgsz": 64, "task": "detect"}, "date": "golden", "version": "reference"}
+    torch.save(ckpt, GOLD / "ckpt_tiny.pt")
+    ref = torch.load(GOLD / "ckpt_tiny.pt", map_location="cpu", weights_only=False)["model"].float().eval()
+    x = seeded((2, 3, 64, 64), 321)
+    with torch.no_grad():
+        y, raw = ref(x)
+    np.savez_compressed(GOLD / "ckpt_tiny_out.npz", y=y.numpy(), **{f"raw{i}": r.numpy() for i, r in enumerate(raw)},
+                        n_params=np.array(sum(p.numel() for p in ref.parameters())))
+    print("ckpt_tiny.pt", (GOLD / "ckpt_tiny.pt").stat().st_size, "bytes")
+
+
 LETTERBOX_CASES = [
     # (src h, src w, new_shape, auto, scaleup, seed)
     (97, 131, (64, 64), False, True, 1),      # downscale, wide
@@ -295,10 +319,14 @@ if __name__ == "__main__":
     if "--only-letterbox" in sys.argv:
         gen_letterbox()
         sys.exit(0)
+    if "--only-ckpt" in sys.argv:
+        gen_checkpoint()
+        sys.exit(0)
     if "--only-val" in sys.argv:
         gen_val_metrics()
         sys.exit(0)
     gen_val_metrics()
+    gen_checkpoint()
     gen_letterbox()
     gen_nms_torchvision()
     gen_nms_reference()
