@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the bs=1 latency measurement")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-launch timing pass (for ncu launch lists)")
     ap.add_argument("--inflight", type=int, default=2,
                     help="batches in flight per GPU (each on its own stream with its own plan buffers)")
     return ap.parse_args()
@@ -372,7 +373,7 @@ def main():
 
     # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager pass
     roof, breakdown = None, None
-    if rank == 0:
+    if rank == 0 and not a.no_roofline:
         model.infer(devx[0])
         torch.cuda.synchronize(dev)
         lt = plan.time_launches(reps=3)
