@@ -27,12 +27,25 @@ for a, b in (("bench.json", "bench.json"), ("bench_ref.json", "bench_reference_a
 bench = json.loads((src / "bench.json").read_text().splitlines()[-1])
 per_step = bench["launches_per_step"]
 
-# launch list + traffic of the last step
-out = subprocess.run([sys.executable, str(ROOT / "tools" / "summarize_launches.py"), str(src / "launches.csv"),
-                      "--last-step", str(per_step)], capture_output=True, text=True)
-(dst / f"{tag}_launches_yolo11n_bs64.md").write_text(out.stdout)
-subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_traffic.py"), str(src / "launches.csv"), "yolo11n_bs64", "--last",
-                str(per_step)], check=False)
+# launch list + traffic of the LAST FULL STEP: the launches from the last image-ingest kernel (stem_*) on
+def last_step_csv(path: Path, n: int) -> Path:
+    lines = path.read_text().splitlines()
+    head = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    rows = list(csv.reader(lines[head + 1:]))
+    hdr = next(csv.reader([lines[head]]))
+    iid, ik = hdr.index("ID"), hdr.index("Kernel Name")
+    starts = sorted({int(r[iid]) for r in rows if len(r) > ik and "stem_" in r[ik]})
+    first = starts[-1]
+    keep = [l for l, r in zip(lines[head + 1:], rows) if len(r) > iid and first <= int(r[iid]) < first + n]
+    out = path.with_name("launches_last_step.csv")
+    out.write_text("\n".join([lines[head]] + keep) + "\n")
+    return out
+
+
+step_csv = last_step_csv(src / "launches.csv", per_step)
+out = subprocess.run([sys.executable, str(ROOT / "tools" / "summarize_launches.py"), str(step_csv)], capture_output=True, text=True)
+(dst / f"{tag}_launches_yolo11n_bs64.md").write_text(out.stdout.replace(str(ROOT) + "/", ""))
+subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_traffic.py"), str(step_csv), "yolo11n_bs64"], check=False)
 
 METRICS = [("gpu__time_duration.sum", "us", 1e-3 if False else None),
            ("dram__bytes_read.sum", "DRAM rd MB", None), ("dram__bytes_write.sum", "DRAM wr MB", None),

@@ -12,7 +12,7 @@ import sys
 from pathlib import Path
 
 KIND = {"conv_tc_kernel": "conv_tc", "stem_conv_kernel": "stem_conv", "dwconv3x3_kernel": "dwconv3x3",
-        "dwconv3x3_mma_kernel": "dwconv3x3", "c3k2_tail_kernel": "c3k2_tail", "letterbox_u8_kernel": "letterbox_u8",
+        "dwconv3x3_mma_kernel": "dwconv3x3", "c3k2_tail_kernel": "c3k2_tail", "stem_fused_kernel": "stem_fused", "letterbox_u8_kernel": "letterbox_u8",
         "psa_attention_kernel": "psa_attention", "sppf_pool_kernel": "sppf_pool", "nms_select_kernel": "nms_select",
         "nms_filter_kernel": "nms_filter", "detect_decode_kernel": "detect_decode"}
 
