@@ -188,6 +188,10 @@ int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream);
  * {gain, padx, pady, w0, h0}. */
 int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream);
 
+/* fp16 -> fp32 elementwise (n elements): ingest of half-precision image tensors, the `.float()` of
+ * engine/predictor.py:83 when the caller hands over an fp16 batch (half the PCIe bytes of fp32). */
+int yl_f16_to_f32(const void* x_f16, float* y, long long n, void* stream);
+
 /* ---- fused stem --------------------------------------------------------------------------------------------- */
 /* Image ingest + layer 0 + layer 1 (cfg/yolo11.yaml:17-18: Conv(3,c0,3,2) -> Conv(c0,c1,3,2), each conv+BN+SiLU,
  * nn/modules/conv.py:47-49) in one kernel: reads the caller's NCHW fp32 batch once, keeps the layer-0 map in

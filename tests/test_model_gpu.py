@@ -223,3 +223,22 @@ def test_predict_pipelined_host_batch_equals_device_batch(golden):
     assert len(r_host) == len(r_dev) == 32
     for a, b in zip(r_host, r_dev):
         assert torch.equal(a.boxes.data, b.boxes.data)
+
+
+def test_predict_fp16_host_tensor_matches_fp32_path():
+    """An fp16 host batch (half the upload) is widened on the device and gives the detections of the same values
+    fed as fp32 (the reference applies `.float()` on the device, engine/predictor.py:83)."""
+    import numpy as np
+    import torch
+
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    x16 = torch.rand(16, 3, 64, 64, generator=torch.Generator().manual_seed(4)).half().pin_memory()
+    r16 = yl.predict(x16, imgsz=64, conf=0.001, verbose=False, device=0, batch=16)
+    r32 = yl.predict(x16.float().pin_memory(), imgsz=64, conf=0.001, verbose=False, device=0, batch=16)
+    assert len(r16) == len(r32) == 16
+    for a, b in zip(r16, r32):
+        assert np.array_equal(a.boxes.data.cpu().numpy(), b.boxes.data.cpu().numpy())

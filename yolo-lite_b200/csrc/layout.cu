@@ -1,5 +1,7 @@
 // Layout kernels either side of the NHWC bf16 core: image ingest (NCHW fp32 -> NHWC bf16), reference-layout
 // export (NHWC -> NCHW fp32), channel-slice copy and nearest 2x upsample.  Pure HBM-bound byte movers.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace yl {
@@ -85,11 +87,38 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
     *reinterpret_cast<uint4*>(y + op * y_cstride + y_coff + g * 8) = v;
 }
 
+// fp16 -> fp32 (8 elements per thread): the ingest of half-precision host tensors (predictor.py:81-84 `.float()`)
+__global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, long long n8,
+                                                         long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+        float4* o = reinterpret_cast<float4*>(y) + 2 * i;
+        o[0] = make_float4(a.x, a.y, b.x, b.y);
+        o[1] = make_float4(c.x, c.y, d.x, d.y);
+    } else if (i == n8) {
+        for (long long j = n8 * 8; j < n; ++j) y[j] = __half2float(x[j]);   // tail (< 8 elements)
+    }
+}
+
 static bool aligned8(const yl_tensor* t) { return t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; }
 
 }  // namespace yl
 
 extern "C" {
+
+int yl_f16_to_f32(const void* x_f16, float* y, long long n, void* stream) {
+    YL_CHECK(x_f16 && y && n >= 0, YL_ERR_ARG, "bad f16_to_f32 arguments");
+    YL_CHECK(((uintptr_t)x_f16 | (uintptr_t)y) % 16 == 0, YL_ERR_ARG, "f16_to_f32 needs 16-byte aligned pointers");
+    if (n == 0) return YL_OK;
+    const long long n8 = n / 8;
+    yl::f16_to_f32_kernel<<<(unsigned)yl::ceil_div64(n8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x_f16), y, n8, n);
+    YL_LAUNCH_OK("f16_to_f32_kernel");
+    return YL_OK;
+}
 
 int yl_nchw_to_nhwc(const float* x_nchw, const yl_tensor* y, void* stream) {
     YL_CHECK(x_nchw && y && y->data, YL_ERR_ARG, "null pointer");

@@ -52,6 +52,19 @@ class LetterBox:
         return cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
 
 
+_POOL = None
+
+
+def _pack_pool():
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) // 2)), thread_name_prefix="yl-pack")
+    return _POOL
+
+
 class _Staging:
     """Grow-only pinned host buffer + device mirror for one letterbox batch (descriptors first, then pixels)."""
 
@@ -105,8 +118,18 @@ def letterbox_batch_cuda(images, new_shape=(640, 640), auto=False, stride=32, de
     base = dev.data_ptr()
     for i, (im, (nw, nh, left, top), off) in enumerate(zip(images, geo, offs)):
         sh, sw = im.shape[:2]
-        hnp[off:off + sh * sw * 3] = np.ascontiguousarray(im).reshape(-1)
         descs[i] = _C.LbImage(base + off, sh, sw, sw * 3, nw, nh, left, top, 0)
+
+    def _pack(i):
+        im, off = images[i], offs[i]
+        hnp[off:off + im.shape[0] * im.shape[1] * 3] = np.ascontiguousarray(im).reshape(-1)
+
+    # the pack into pinned memory is a plain memcpy (numpy releases the GIL): spread large batches over a few threads
+    if n >= 4 and total > (8 << 20):
+        list(_pack_pool().map(_pack, range(n)))
+    else:
+        for i in range(n):
+            _pack(i)
     hnp[: n * C.sizeof(_C.LbImage)] = np.frombuffer(descs, dtype=np.uint8)
     with torch.cuda.device(device):
         dev[:total].copy_(host[:total], non_blocking=True)

@@ -96,8 +96,8 @@ class DetectionPredictor:
 
     def _chunking(self, im):
         """Number of ingest chunks for a host tensor batch (1 = plain path)."""
-        if not isinstance(im, torch.Tensor) or im.is_cuda or im.dim() != 4 or im.dtype != torch.float32 \
-                or not im.is_contiguous():
+        if not isinstance(im, torch.Tensor) or im.is_cuda or im.dim() != 4 \
+                or im.dtype not in (torch.float32, torch.float16) or not im.is_contiguous():
             return 1
         b = im.shape[0]
         for n in range(int(self.pipeline_chunks), 1, -1):
@@ -112,12 +112,14 @@ class DetectionPredictor:
         dev = self.device
         B = im_host.shape[0]
         cb = B // n_chunks
-        key = (tuple(im_host.shape), a.max_det)
+        half = im_host.dtype == torch.float16     # half the PCIe bytes; widened on the device (predictor.py:83 `.float()`)
+        key = (tuple(im_host.shape), a.max_det, half)
         # the staging state lives on the backend: YOLOLite.predict builds a fresh predictor per call, but the pinned
         # upload pipeline (two device staging batches, streams, events) must survive across calls
         st = self.model.__dict__.get("_yl_pipe_state")
         if st is None or st["key"] != key:
             st = {"key": key, "bufs": [torch.empty(im_host.shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                  "raw": [torch.empty(im_host.shape, dtype=torch.float16, device=dev) for _ in range(2)] if half else None,
                   "free": [None, None], "turn": 0,
                   "dets": torch.empty((B, a.max_det, 6), dtype=torch.float32, device=dev),
                   "counts": torch.empty((B,), dtype=torch.int32, device=dev),
@@ -137,11 +139,13 @@ class DetectionPredictor:
         # calls ago): it overlaps the previous call's kernels and the caller's host-side work.
         if st["free"][j] is not None:
             st["copy"].wait_event(st["free"][j])
+        land = st["raw"][j] if half else buf      # where the upload lands
         with torch.cuda.stream(st["copy"]):
             for k in range(n_chunks):
-                buf[k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
+                land[k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
                 st["events"][k].record(st["copy"])
         model = self.model.model
+        lib = _C.load()
         fly = max(1, min(int(self.in_flight), n_chunks, 2))
         lanes = st["lanes"][:fly]
         for ln in lanes:
@@ -151,6 +155,10 @@ class DetectionPredictor:
             ln = lanes[k % fly]
             with torch.cuda.stream(ln):
                 ln.wait_event(st["events"][k])
+                if half:
+                    src, dstc = land[k * cb:(k + 1) * cb], buf[k * cb:(k + 1) * cb]
+                    _C.check(lib.yl_f16_to_f32(src.data_ptr(), dstc.data_ptr(), dstc.numel(), _C.stream_ptr()),
+                             "yl_f16_to_f32")
                 y, _ = model.infer(buf[k * cb:(k + 1) * cb], slot=k % fly)
                 ops.nms_padded(y, a.conf, a.iou, a.classes, a.agnostic_nms, False, a.max_det,
                                out=st["dets"][k * cb:(k + 1) * cb], counts=st["counts"][k * cb:(k + 1) * cb])
