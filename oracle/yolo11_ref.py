@@ -138,11 +138,12 @@ def decode(raw, strides=STRIDES, reg_max=REG_MAX):
         gy, gx = torch.meshgrid(sy, sx, indexing="ij")
         anchors.append(torch.stack((gx, gy), -1).view(-1, 2))
         svec.append(torch.full((h * w, 1), float(s)))
-    anchors = torch.cat(anchors).t()          # (2, A)
-    svec = torch.cat(svec).t()                # (1, A)
+    dev = raw[0].device                       # CPU in every test; tools/eager_gpu_baseline.py runs it on CUDA
+    anchors = torch.cat(anchors).t().to(dev)  # (2, A)
+    svec = torch.cat(svec).t().to(dev)        # (1, A)
     box, cls = x_cat.split((reg_max * 4, no - reg_max * 4), 1)
     a = box.shape[-1]
-    proj = torch.arange(reg_max, dtype=torch.float32)
+    proj = torch.arange(reg_max, dtype=torch.float32, device=dev)
     dist = (box.view(B, 4, reg_max, a).transpose(2, 1).softmax(1) * proj.view(1, reg_max, 1, 1)).sum(1)
     lt, rb = dist.chunk(2, 1)
     x1y1 = anchors.unsqueeze(0) - lt
