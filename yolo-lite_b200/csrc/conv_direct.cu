@@ -730,21 +730,32 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_16816(acc[nt], a[ks], bfrag[ks][nt][0], bfrag[ks][nt][1]);
         }
-        // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8
+        // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8.  Pairs of n-tiles are transposed inside each lane quad (items:
+        // (g, nt), (g, nt+1), (g+8, nt), (g+8, nt+1); lane t ends up with the 16 bytes of item t), so a lane stores 8
+        // channels at once and a quad writes 2 x 32 contiguous bytes instead of sixteen scattered 4-byte stores
+        const int swo = w0 + wl0 + g + 8 * (t >> 1);
+        const bool st_ok = swo < Wo;
+        __nv_bfloat16* dst = yrow + (long long)swo * y_cstride + 8 * (t & 1);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int wo = w0 + wl0 + g + half * 8;
-            if (wo >= Wo) continue;
-            __nv_bfloat16* dst = yrow + (long long)wo * y_cstride + 2 * t;
+        for (int np = 0; np < NT / 2; ++np) {
+            float e[2][4];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                float v0 = acc[nt][half * 2 + 0], v1 = acc[nt][half * 2 + 1];
-                if (act) {
-                    v0 = silu_f(v0);
-                    v1 = silu_f(v1);
-                }
-                *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16x2(v0, v1);
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) e[q][i] = act ? silu_fast(acc[2 * np + q][i]) : acc[2 * np + q][i];
+            uint32_t v0 = pack_bf16x2(e[0][0], e[0][1]), v1 = pack_bf16x2(e[1][0], e[1][1]);
+            uint32_t v2 = pack_bf16x2(e[0][2], e[0][3]), v3 = pack_bf16x2(e[1][2], e[1][3]);
+            {
+                const uint32_t s0 = (t & 1) ? v0 : v1, s1 = (t & 1) ? v2 : v3;
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                if (t & 1) { v0 = r0; v2 = r1; } else { v1 = r0; v3 = r1; }
             }
+            {
+                const uint32_t s0 = (t & 2) ? v0 : v2, s1 = (t & 2) ? v1 : v3;
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+                if (t & 2) { v0 = r0; v1 = r1; } else { v2 = r0; v3 = r1; }
+            }
+            if (st_ok) *reinterpret_cast<uint4*>(dst + np * 16) = make_uint4(v0, v1, v2, v3);
         }
     }
 }
