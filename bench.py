@@ -172,6 +172,30 @@ def peaks():
     return 6650.0, 1400.0, "fallback"
 
 
+def pin_to_gpu_numa(local):
+    """Bind this rank (and therefore the first-touch placement of its pinned host buffers) to the CPU cores NVML
+    reports as local to its GPU: with one process per GPU on a multi-socket host, uploads otherwise cross the
+    inter-socket link for half of the ranks.  Returns (all_cpus, chosen_cpus) or None when unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allc = os.sched_getaffinity(0)
+        cpus &= allc
+        if cpus and cpus != allc:
+            os.sched_setaffinity(0, cpus)
+            return allc, cpus
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     a = parse()
@@ -225,6 +249,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -450,6 +475,8 @@ def main():
 
     cpu_b = None
     if rank == 0 and not a.no_cpu_baseline:
+        if numa is not None:
+            os.sched_setaffinity(0, numa[0])            # the CPU baseline may use every host core again
         threads = max(1, min(os.cpu_count() or 1, 64))
         torch.set_num_threads(threads)
         v, ts = time_cpu(sd_cpu, 8, reps=3, warm=1, budget_s=12.0)
@@ -466,6 +493,7 @@ def main():
             "bs1_latency_ms": lat,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "global_batch": a.batch * world, "parallelism": f"dp{world} batch-sharded, no collective",
+                       "cpu_affinity": (f"rank bound to the {len(numa[1])} cores NVML reports local to its GPU" if numa else "default"),
                        "in_flight": f"{n_fly} batches in flight per GPU (one stream + one plan slot each)",
                        "l2": f"{n_sets} rotating input batches of {a.batch * 3 * IMG * IMG * 4 / 1e6:.0f} MB each (> L2)",
                        "weights": "random init from cfg/yolo11.yaml, BN statistics randomised (seed 1)"},
