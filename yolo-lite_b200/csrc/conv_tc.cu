@@ -758,7 +758,14 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
 
     // N tiling
     const int co16 = ceil_div(y.c, 16) * 16;
-    const int n_tiles = ceil_div(co16, 256);
+    int n_tiles = ceil_div(co16, 256);
+    // A 129..256-wide tile needs all 512 TMEM columns for its two accumulator stages, i.e. one CTA per SM.  When the
+    // M tiling then yields between one and two waves of CTAs (20x20 maps at bs = 64: 200 tiles on 148 SMs), the
+    // second wave runs almost alone; halving the tile (2 CTAs/SM, 256 columns each) keeps every tile resident at once.
+    {
+        const long long m_est = ceil_div64((long long)x.n * Ho * Wo, 128);
+        if (n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && env_int("YL_NSPLIT", 1)) n_tiles = 2;
+    }
     p.co_tile = ceil_div(ceil_div(co16, n_tiles), 16) * 16;
 
     // halo-patch mode: 3x3 stride-1 convs on thin inputs are L2->SM bound when every tap is fetched separately
