@@ -242,3 +242,29 @@ def test_predict_fp16_host_tensor_matches_fp32_path():
     assert len(r16) == len(r32) == 16
     for a, b in zip(r16, r32):
         assert np.array_equal(a.boxes.data.cpu().numpy(), b.boxes.data.cpu().numpy())
+
+
+def test_async_host_predict_then_device_predict_do_not_race():
+    """A device-tensor predict (plain path, caller's stream) right after an asynchronous host-tensor predict shares
+    the plan slots with it: both must still produce the detections of their own batch."""
+    import numpy as np
+    import torch
+
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    g = torch.Generator().manual_seed(8)
+    xa = torch.rand(16, 3, 64, 64, generator=g).pin_memory()
+    xb = torch.rand(16, 3, 64, 64, generator=g)
+    kw = dict(imgsz=64, conf=0.001, verbose=False, device=0, batch=16)
+    ref_a = [r.boxes.data.cpu().numpy() for r in yl.predict(xa, **kw)]
+    ref_b = [r.boxes.data.cpu().numpy() for r in yl.predict(xb.cuda(), **kw)]
+    for _ in range(5):
+        ra = yl.predict(xa, **kw)                 # asynchronous: only enqueued
+        rb = yl.predict(xb.cuda(), **kw)          # plain path, immediately behind it
+        for r, want in zip(ra, ref_a):
+            assert np.array_equal(r.boxes.data.cpu().numpy(), want)
+        for r, want in zip(rb, ref_b):
+            assert np.array_equal(r.boxes.data.cpu().numpy(), want)

@@ -139,6 +139,11 @@ class DetectionPredictor:
         # calls ago): it overlaps the previous call's kernels and the caller's host-side work.
         if st["free"][j] is not None:
             st["copy"].wait_event(st["free"][j])
+        # order the pipeline after whatever the caller (or a plain-path predict on a device tensor, which shares the
+        # plan slots) has already queued on the current stream; in the steady pattern that stream is idle here
+        main = torch.cuda.current_stream(dev)
+        for side in (st["copy"], *st["lanes"]):
+            side.wait_stream(main)
         land = st["raw"][j] if half else buf      # where the upload lands
         with torch.cuda.stream(st["copy"]):
             for k in range(n_chunks):
@@ -250,6 +255,11 @@ class DetectionPredictor:
                     with profilers[2]:
                         self.results = self.postprocess(None, im, im0s, nms_out=(dets, counts), stream=post)
                 else:
+                    st = self.model.__dict__.get("_yl_pipe_state")
+                    if st is not None:     # an asynchronous host-tensor batch may still own the plan slots
+                        cur = torch.cuda.current_stream(self.device)
+                        for side in (*st["lanes"], st["post"]):
+                            cur.wait_stream(side)
                     with profilers[0]:
                         im = self.preprocess(im0s)
                     with profilers[1]:
