@@ -101,7 +101,9 @@ class Builder:
             for v in views:
                 if v is None:
                     continue
-                if isinstance(v, torch.Tensor):
+                if isinstance(v, tuple):            # (tensor, lo, hi): an explicit sub-range of a plain tensor
+                    key, c0, c1 = v[0].data_ptr(), int(v[1]), int(v[2])
+                elif isinstance(v, torch.Tensor):
                     key, c0, c1 = v.data_ptr(), 0, 1 << 30
                 else:
                     key, c0, c1 = v.buf.data_ptr(), v.coff, v.coff + v.c
@@ -199,7 +201,12 @@ class Builder:
                    desc=f"{x.c}->{pc.co} k{k}s{stride} {x.h}x{x.w}" + (" +res" if res is not None else "")
                    + (" up2" if upsample else "") + (" +up2" if y_up is not None else "")
                    + (" f32" if esz == 4 and store else "") + (" +decode" if det is not None else ""),
-                   reads=(x, res), writes=(y if store else None, y_up))
+                   reads=(x, res),
+                   # the fused decode writes its own block of the prediction: rows (box | class) x this level's anchors;
+                   # blocks of different launches are disjoint, a reader of the whole tensor (NMS) depends on all of them
+                   writes=(y if store else None, y_up,
+                           None if det is None else (det.pred, 2 * det.anchor0 + (det.mode == _C.DET_CLS),
+                                                     2 * det.anchor0 + (det.mode == _C.DET_CLS) + 1)))
         return y if store else None
 
     def stem_fused(self, x: NchwInput, pc0: PackedConv, pc1: PackedConv, act0: bool, act1: bool, out=None) -> View:
@@ -273,6 +280,25 @@ class Builder:
                    kind="detect_decode", bytes_=n * a * ((4 * reg_max + nc) * 4 + (4 + nc) * 4), reads=tuple(levels),
                    writes=(y,))
         return y
+
+    def nms(self, pred: torch.Tensor, conf, iou, classes=None, agnostic=False, multi_label=False, max_det=300,
+            max_nms=30000, max_wh=7680.0):
+        """Batched NMS as the last launches of the plan (so a whole step is the ingest + ONE graph launch): the
+        workspace, (B, max_det, 6) detections and (B,) counts are plan-owned static buffers."""
+        B, C4, A = pred.shape
+        nc = C4 - 4
+        ws = torch.empty(max(int(self.lib.yl_nms_workspace_bytes(B, A, nc, int(multi_label))), 16), dtype=torch.uint8,
+                         device=self.device)
+        out = torch.empty((B, max_det, 6), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        cls_t = None if classes is None else torch.as_tensor(list(classes), dtype=torch.int32).to(self.device)
+        self.buffers += [ws, out, counts]
+        self._push(self.lib.yl_nms_batched, pred.data_ptr(), B, nc, A, float(conf), float(iou),
+                   None if cls_t is None else cls_t.data_ptr(), 0 if cls_t is None else cls_t.numel(), int(agnostic),
+                   int(multi_label), int(max_det), int(max_nms), float(max_wh), ws.data_ptr(), ws.numel(), out.data_ptr(),
+                   counts.data_ptr(), keep=(ws, out, counts, cls_t, pred), kind="nms", bytes_=B * C4 * A * 4,
+                   desc=f"conf {conf} iou {iou} max_det {max_det}", reads=(pred,), writes=(out, counts, ws))
+        return out, counts
 
     def to_nchw(self, x: View) -> torch.Tensor:
         x = self.mat(x)

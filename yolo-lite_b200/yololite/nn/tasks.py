@@ -327,9 +327,11 @@ class BaseModel(YLModule):
         memo[k] = c
         return c
 
-    def _get_plan(self, shape, dev, want_raw=False, slot=0):
+    def _get_plan(self, shape, dev, want_raw=False, slot=0, nms=None):
+        """`nms`: None or the hashable argument tuple of Builder.nms: the plan then ends with the batched NMS and its
+        entry carries (dets, counts) instead of the raw head maps."""
         plans = self.__dict__.setdefault("_yl_plans", {})
-        key = (tuple(shape), dev.index, bool(self.use_cuda_graph), bool(want_raw), int(slot))
+        key = (tuple(shape), dev.index, bool(self.use_cuda_graph), bool(want_raw), int(slot), nms)
         entry = plans.get(key)
         if entry is None:
             with torch.cuda.device(dev):
@@ -338,11 +340,12 @@ class BaseModel(YLModule):
                 static_in = torch.zeros(tuple(shape), dtype=torch.float32, device=dev)
                 xin = g.input_nchw(static_in)
                 y, raws = self._emit(g, xin)
+                post = g.nms(y, *nms) if nms is not None else None
                 plan = g.finish()
                 if self.use_cuda_graph:
                     plan.capture(skip=1)     # the image ingest stays eager so it can read the caller's tensor
                 raw_views = [r.buf.permute(0, 3, 1, 2) for r in raws]   # (B, no, H, W) views, zero-copy
-                entry = (plan, static_in, y, raw_views)
+                entry = (plan, static_in, y, raw_views if post is None else post)
             plans[key] = entry
         return entry
 
@@ -377,6 +380,30 @@ class BaseModel(YLModule):
                 static_in.copy_(x, non_blocking=True)
                 plan.run()
         return y, raws
+
+    @torch.no_grad()
+    def infer_nms(self, x: torch.Tensor, conf=0.25, iou=0.45, classes=None, agnostic=False, multi_label=False,
+                  max_det=300, max_nms=30000, max_wh=7680.0, slot: int = 0):
+        """Engine entry for a whole step: NCHW float batch on CUDA -> (dets (B, max_det, 6), counts (B,) int32), the
+        padded output of `ops.nms_padded(self.infer(x)[0], ...)`, with the NMS kernels recorded in the same plan /
+        CUDA graph as the model (ingest + one graph launch per step).  The returned tensors alias plan buffers and
+        are overwritten by the next call with the same shape, arguments and slot."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or not x.is_cuda:
+            raise RuntimeError("infer_nms expects a (B, C, H, W) CUDA tensor (yololite has no CPU fallback)")
+        dev = x.device
+        s = int(self.stride.max()) if hasattr(self, "stride") else 32
+        if x.shape[2] % s or x.shape[3] % s:
+            raise ValueError(f"image size {tuple(x.shape[2:])} must be a multiple of the model stride {s}")
+        nms = (float(conf), float(iou), None if classes is None else tuple(int(c) for c in classes), bool(agnostic),
+               bool(multi_label), int(max_det), int(max_nms), float(max_wh))
+        plan, static_in, _, post = self._get_plan(x.shape, dev, False, slot, nms)
+        with torch.cuda.device(dev):
+            if x.dtype == torch.float32 and x.is_contiguous():
+                plan.run(ingest_ptr=x.data_ptr())
+            else:
+                static_in.copy_(x, non_blocking=True)
+                plan.run()
+        return post
 
     def fuse(self, verbose=True):
         """Reference API (AutoBackend calls model.fuse(), autobackend.py:74; the reference deleted the method
