@@ -268,3 +268,31 @@ def test_async_host_predict_then_device_predict_do_not_race():
             assert np.array_equal(r.boxes.data.cpu().numpy(), want)
         for r, want in zip(rb, ref_b):
             assert np.array_equal(r.boxes.data.cpu().numpy(), want)
+
+
+def test_infer_nms_equals_infer_then_nms():
+    """The in-plan NMS (one CUDA graph per step) returns exactly what infer() + ops.nms_padded() return."""
+    import numpy as np
+    import torch
+
+    from oracle.weights import fill_state_dict_
+    from yololite.nn.tasks import DetectionModel
+    from yololite.utils import ops
+
+    m = fill_state_dict_(DetectionModel("yolo11n.yaml", verbose=False)).eval().cuda()
+    x = torch.rand(3, 3, 96, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    for kw in (dict(conf=0.001, iou=0.7), dict(conf=0.05, iou=0.45, classes=[0, 3, 7], max_det=50),
+               dict(conf=0.001, iou=0.6, agnostic=True, multi_label=True)):
+        y, _ = m.infer(x)
+        d0, c0 = ops.nms_padded(y.clone(), kw.get("conf"), kw.get("iou"), kw.get("classes"), kw.get("agnostic", False),
+                                kw.get("multi_label", False), kw.get("max_det", 300))
+        d1, c1 = m.infer_nms(x, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(c0, c1), kw
+        n = c0.tolist()
+        for i in range(3):
+            assert np.array_equal(d0[i, : n[i]].cpu().numpy(), d1[i, : n[i]].cpu().numpy()), (kw, i)
+        # a second call with the same arguments replays the same plan (and must not depend on stale scratch)
+        d2, c2 = m.infer_nms(x, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(c1, c2)
