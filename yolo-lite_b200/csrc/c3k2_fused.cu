@@ -59,7 +59,9 @@ __host__ __device__ constexpr int pitch16(int data_bytes) { return data_bytes + 
 template <int C>
 struct C3k2Smem {
     static constexpr int CH = C / 2;                  // hidden channels of the bottleneck
-    static constexpr int TH = 8, TW = 16;
+    // tile rows: 16 for the thin variant (less halo per output pixel, 21 of 24 stage-A slots busy, half the barriers
+    // per pixel; its smem still allows the 2 CTAs/SM its registers allow), 8 otherwise (two CTAs/SM need <= 113 KB)
+    static constexpr int TH = (C == 16) ? 16 : 8, TW = 16;
     static constexpr int PH = TH + 4, PW = TW + 4;    // patch of t
     static constexpr int HH = TH + 2, HW = TW + 2;    // region of h
     static constexpr int TS = pitch16(4 * C);         // bytes per patch pixel (2C bf16)
@@ -242,8 +244,7 @@ __global__ void __launch_bounds__(256, 2) c3k2_tail_kernel(const C3k2TailParams 
         __syncthreads();
 
         // ================= stage B: y2 = y1 + SiLU(conv3x3(h) + bb), warp = tile row =================
-        {
-            const int r = warp;   // 8 warps <-> TH = 8 rows
+        for (int r = warp; r < TH; r += 8) {   // warp = tile row(s)
             constexpr int NT = C / 8;
             float acc[NT][4];
 #pragma unroll
@@ -316,14 +317,15 @@ __global__ void __launch_bounds__(256, 2) c3k2_tail_kernel(const C3k2TailParams 
         __syncthreads();   // stage C reads y2 rows written by other warps
 
         // ================= stage C: out = SiLU(conv1x1([y0 y1 y2]) + b2) =================
-        // warp = (32-channel group `grp`, rows rblk*NG .. +NG): the weights are the stationary register operand,
+        // warp = (32-channel group `grp`, a block of TH*NG/8 rows): the weights are the stationary register operand,
         // the activations stream through ldmatrix (KC loads feed 4*KC MMAs)
         {
             // after the quad transpose lane t stores pixel col g + 8 * (t >> 1), channels 16 * np + 8 * (t & 1) ..+8
             const int scol = g + 8 * (t >> 1);
             const int wi = w0 + scol;
-            for (int rr = 0; rr < NG; ++rr) {
-                const int r = rblk * NG + rr;
+            const int rpw = TH * NG / 8;          // rows per warp: the 8 / NG warps of a channel group share the TH rows
+            for (int rr = 0; rr < rpw; ++rr) {
+                const int r = rblk * rpw + rr;
                 uint32_t a[KC][4];
                 const uint32_t trow = sTc + (uint32_t)(((r + 2) * PW + lrow + 2) * TS + 8 * khalf * 2);
                 const uint32_t yrow = sY2 + (uint32_t)((r * TW + lrow) * YS + 8 * khalf * 2);
@@ -371,8 +373,11 @@ __global__ void __launch_bounds__(256, 2) c3k2_tail_kernel(const C3k2TailParams 
 static int g_c3k2_sms = 0;
 
 template <int C>
-static int launch_c3k2_tail(const C3k2TailParams& p, cudaStream_t s) {
+static int launch_c3k2_tail(C3k2TailParams p, cudaStream_t s) {
     using S = C3k2Smem<C>;
+    p.tiles_w = ceil_div(p.W, S::TW);
+    p.tiles_h = ceil_div(p.H, S::TH);
+    p.total_tiles = p.tiles_w * p.tiles_h * p.N;
     const size_t smem = (size_t)S::total(p.C2);
     static size_t attr_set = 0;
     if (smem > attr_set) {
@@ -438,9 +443,6 @@ extern "C" int yl_c3k2_tail(const yl_tensor* t, const yl_tensor* y, const void* 
     p.W = t->w;
     p.C2 = y->c;
     p.add = shortcut;
-    p.tiles_w = yl::ceil_div(t->w, 16);
-    p.tiles_h = yl::ceil_div(t->h, 8);
-    p.total_tiles = p.tiles_w * p.tiles_h * t->n;
     cudaStream_t s = (cudaStream_t)stream;
     return c == 16 ? yl::launch_c3k2_tail<16>(p, s) : yl::launch_c3k2_tail<32>(p, s);
 }
