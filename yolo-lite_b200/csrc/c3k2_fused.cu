@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256, 2) c3k2_tail_kernel(const C3k2TailParams 
     }
 }
 
-static int g_c3k2_sms = 0;
+static int g_c3k2_sms = 148, g_c3k2_max_smem = 0;
 
 template <int C>
 static int launch_c3k2_tail(C3k2TailParams p, cudaStream_t s) {
@@ -379,22 +379,25 @@ static int launch_c3k2_tail(C3k2TailParams p, cudaStream_t s) {
     p.tiles_h = ceil_div(p.H, S::TH);
     p.total_tiles = p.tiles_w * p.tiles_h * p.N;
     const size_t smem = (size_t)S::total(p.C2);
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        YL_CUDA(cudaFuncSetAttribute(c3k2_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
-    if (!g_c3k2_sms) {
-        int dev = 0;
-        YL_CUDA(cudaGetDevice(&dev));
-        YL_CUDA(cudaDeviceGetAttribute(&g_c3k2_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    YL_CHECK((int)smem <= g_c3k2_max_smem, YL_ERR_UNSUPPORTED, "c3k2 tail needs %zu B of shared memory (device allows %d)", smem,
+             g_c3k2_max_smem);
     int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);   // __launch_bounds__(256, 2): registers cap residency at 2
     int grid = g_c3k2_sms * per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
     YL_CUDA(launch_kernel(c3k2_tail_kernel<C>, dim3(grid), dim3(256), smem, s, p));
     YL_LAUNCH_OK("c3k2_tail_kernel");
+    return YL_OK;
+}
+
+// per-device setup (called by yl_init): opt both instantiations into the device's full dynamic shared memory
+int init_c3k2() {
+    int dev = 0;
+    YL_CUDA(cudaGetDevice(&dev));
+    YL_CUDA(cudaDeviceGetAttribute(&g_c3k2_sms, cudaDevAttrMultiProcessorCount, dev));
+    YL_CUDA(cudaDeviceGetAttribute(&g_c3k2_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    YL_CUDA(cudaFuncSetAttribute(c3k2_tail_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_c3k2_max_smem));
+    YL_CUDA(cudaFuncSetAttribute(c3k2_tail_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_c3k2_max_smem));
     return YL_OK;
 }
 

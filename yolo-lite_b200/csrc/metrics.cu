@@ -77,6 +77,12 @@ __global__ void __launch_bounds__(256) match_predictions_kernel(const float* __r
     for (int i = D * nthr + threadIdx.x; i < max_det * nthr; i += blockDim.x) tp[(long long)b * max_det * nthr + i] = 0;
 }
 
+// per-device setup (called by yl_init): crowded images need more than the default 48 KB of dynamic shared memory
+int init_metrics() {
+    YL_CUDA(cudaFuncSetAttribute(match_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return YL_OK;
+}
+
 }  // namespace yl
 
 extern "C" int yl_match_predictions(const float* dets, const int32_t* counts, int B, int max_det, const float* gt_boxes,
@@ -87,13 +93,6 @@ extern "C" int yl_match_predictions(const float* dets, const int32_t* counts, in
     YL_CHECK(max_labels_per_image >= 0, YL_ERR_ARG, "bad label count");
     const size_t smem = ((size_t)n_thresholds * max_labels_per_image + max_det) * sizeof(int32_t);
     YL_CHECK(smem <= 200 * 1024, YL_ERR_UNSUPPORTED, "too many labels per image for the matching kernel (%d)", max_labels_per_image);
-    if (smem > 48 * 1024) {
-        static size_t attr = 0;
-        if (smem > attr) {
-            YL_CUDA(cudaFuncSetAttribute(yl::match_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
-    }
     yl::match_predictions_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(dets, counts, max_det, gt_boxes, gt_cls, gt_offsets,
                                                                          iou_thresholds_dev, n_thresholds, 1e-7f, tp);
     YL_LAUNCH_OK("match_predictions_kernel");

@@ -41,6 +41,9 @@ int init_conv_tc();    // conv_tc.cu
 int init_nms();        // nms.cu
 int init_attention();  // attention.cu
 int init_pool();       // pool.cu
+int init_c3k2();       // c3k2_fused.cu
+int init_stem_fused(); // stem_fused.cu
+int init_metrics();    // metrics.cu
 
 }  // namespace yl
 
@@ -84,6 +87,9 @@ int yl_init(int device) {
     if ((rc = yl::init_nms()) != 0) return rc;
     if ((rc = yl::init_attention()) != 0) return rc;
     if ((rc = yl::init_pool()) != 0) return rc;
+    if ((rc = yl::init_c3k2()) != 0) return rc;
+    if ((rc = yl::init_stem_fused()) != 0) return rc;
+    if ((rc = yl::init_metrics()) != 0) return rc;
     yl::g_device = device;
     return YL_OK;
 }

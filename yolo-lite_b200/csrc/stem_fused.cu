@@ -335,6 +335,17 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
     }
 }
 
+static int g_sf_sms = 148;
+
+// per-device setup (called by yl_init)
+int init_stem_fused() {
+    int dev = 0;
+    YL_CUDA(cudaGetDevice(&dev));
+    YL_CUDA(cudaDeviceGetAttribute(&g_sf_sms, cudaDevAttrMultiProcessorCount, dev));
+    YL_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    return YL_OK;
+}
+
 }  // namespace yl
 
 extern "C" int yl_stem_fused_supported(int ci, int c0, int c1) { return ci >= 1 && ci <= 3 && c0 == 16 && c1 == 32; }
@@ -376,14 +387,7 @@ extern "C" int yl_stem_fused(const float* x_nchw, int n, int ci, int h, int w, c
     p.tiles_w = yl::ceil_div(W1, yl::SF_TW);
     p.tiles_h = yl::ceil_div(H1, yl::SF_TH);
     p.total_tiles = p.tiles_w * p.tiles_h * n;
-    static bool attr_set = false;
-    if (!attr_set) {
-        YL_CUDA(cudaFuncSetAttribute(yl::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, yl::SF_SMEM));
-        attr_set = true;
-    }
-    int dev = 0, sms = 148;
-    YL_CUDA(cudaGetDevice(&dev));
-    YL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = yl::g_sf_sms;
     int per_sm = (int)((size_t)220 * 1024 / (yl::SF_SMEM + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
     int grid = sms * per_sm;
