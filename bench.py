@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the bs=1 latency measurement")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-launch timing pass (for ncu launch lists)")
+    ap.add_argument("--repeats", type=int, default=5, help="repeat the K-step timed region; value = the median repeat")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary BASELINE configs (yolo11m bs=256 sharded, NMS stress, eager GPU baseline, H2D ceiling)")
     ap.add_argument("--inflight", type=int, default=2,
                     help="batches in flight per GPU (each on its own stream with its own plan buffers)")
     return ap.parse_args()
@@ -196,6 +199,150 @@ def pin_to_gpu_numa(local):
     return None
 
 
+
+# ------------------------------------------------------------------------------------------------ secondary configs
+def bench_yolo11m_sharded(dev, rank, world, dist, ydist, steps=6, warm=3, total=256):
+    """BASELINE config 4: yolo11m (random init from the yaml), synthetic 640x640, GLOBAL batch 256 sharded over the ranks
+    (strong scaling: 256 / N images per GPU), same step as the headline (ingest + model + decode + batched NMS, two
+    batches in flight).  Rank 0 adds the conv kernel's roofline / tensor-pipe fraction from per-launch event timing."""
+    from yololite.nn.tasks import DetectionModel
+
+    b = total // world
+    torch.manual_seed(0)
+    m = randomise_model_(DetectionModel("yolo11m.yaml", verbose=False)).eval().to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    xs = [torch.rand(b, 3, IMG, IMG, generator=g).to(dev) for _ in range(2)]
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+    def run(k):
+        main = torch.cuda.current_stream(dev)
+        for s_ in lanes:
+            s_.wait_stream(main)
+        for i in range(k):
+            with torch.cuda.stream(lanes[i % 2]):
+                out = m.infer_nms(xs[i % 2], CONF, IOU, None, False, False, MAX_DET, slot=i % 2)
+        for s_ in lanes:
+            main.wait_stream(s_)
+        return out
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    run(2 * warm)
+    barrier()
+    times = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        dets, counts = run(steps)
+        e1.record()
+        barrier()
+        times.append(ydist.max_over_ranks(e0.elapsed_time(e1), dev))
+    ms = statistics.median(times)
+    out = {"value": round(total * steps / (ms / 1e3), 1), "unit": "images/s", "scaling": "strong",
+           "global_batch": total, "per_gpu_batch": b, "steps": steps, "warmup": warm, "ms_per_step": round(ms / steps, 4),
+           "runs_ms": [round(t, 3) for t in times], "in_flight": 2, "detections_last_step_rank0": int(counts.sum().item()),
+           "workload": f"yolo11m synthetic {IMG}x{IMG}, global bs={total} sharded {b}/GPU over {world} GPU(s), predict NMS"}
+    if rank == 0:
+        nms_key = (float(CONF), float(IOU), None, False, False, int(MAX_DET), 30000, 7680.0)
+        plan = m._get_plan(xs[0].shape, dev, False, 0, nms_key)[0]
+        lt = plan.time_launches(reps=1, inner=2)
+        hbm, tf, _ = peaks()
+        tot = {"ms": 0.0, "bytes": 0, "flops": 0, "n": 0}
+        all_ms = 0.0
+        for md, t in zip(plan.meta, lt):
+            all_ms += t
+            if md["kind"] == "conv_tc":
+                tot["ms"] += t
+                tot["bytes"] += md["bytes"]
+                tot["flops"] += md["flops"]
+                tot["n"] += 1
+        out["conv_tc"] = {"launches": tot["n"], "ms": round(tot["ms"], 3), "share_of_step": round(tot["ms"] / all_ms, 3),
+                          "achieved_GBps": round(tot["bytes"] / 1e9 / (tot["ms"] / 1e3), 1),
+                          "hbm_frac": round(tot["bytes"] / 1e9 / (tot["ms"] / 1e3) / hbm, 4),
+                          "tensor_tflops": round(tot["flops"] / 1e12 / (tot["ms"] / 1e3), 1),
+                          "tensor_frac": round(tot["flops"] / 1e12 / (tot["ms"] / 1e3) / tf, 4), "tensor_peak_tflops": tf}
+    del m, xs
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_nms_stress(dev, B=256, A=8400, nc=80):
+    """BASELINE config 5: NMS stress at B=256, A=8400, nc=80, conf=0.001, iou=0.7, max_det=300 (SURVEY 8d inputs: dense =
+    every anchor a candidate, multi-label > 30000 pairs -> the max_nms path; sparse = ~2.7 % of anchors), both label
+    modes.  Algorithmic bytes = the (B, 84, A) fp32 prediction read once = 722 MB; time = the whole yl_nms_batched call
+    (filter + select kernels), CUDA events, median of 5."""
+    from yololite.utils import ops
+
+    hbm = peaks()[0]
+    res = {"algorithmic_MB": round(B * (4 + nc) * A * 4 / 1e6, 1), "B": B, "A": A, "nc": nc, "conf": 0.001, "iou": IOU,
+           "max_det": MAX_DET, "cases": {}}
+    for regime, (mean, std) in (("dense", (-5.0, 2.0)), ("sparse", (-12.0, 1.5))):
+        g = torch.Generator(device=dev).manual_seed(2)
+        pred = torch.empty((B, 4 + nc, A), device=dev)
+        pred[:, 0:2] = torch.rand((B, 2, A), device=dev, generator=g) * 640
+        pred[:, 2:4] = torch.rand((B, 2, A), device=dev, generator=g) * 248 + 8
+        pred[:, 4:] = torch.sigmoid(torch.randn((B, nc, A), device=dev, generator=g) * std + mean)
+        cand = int((pred[:, 4:].amax(1) > 0.001).sum().item())
+        for multi in (False, True):
+            ts = []
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dets, counts = ops.nms_batched(pred, 0.001, IOU, multi_label=multi, max_det=MAX_DET)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            gbs = B * (4 + nc) * A * 4 / 1e9 / (ms / 1e3)
+            res["cases"][f"{regime}_{'multi' if multi else 'single'}_label"] = {
+                "ms": round(ms, 4), "achieved_GBps": round(gbs, 1), "hbm_frac": round(gbs / hbm, 4),
+                "candidate_anchors_per_image": round(cand / B, 1), "detections": int(counts.sum().item())}
+        # the filter kernel alone: conf = 1.0 leaves no candidate, so the select kernel has nothing to do
+        ts = []
+        for i in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.nms_batched(pred, 1.0, IOU, max_det=MAX_DET)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.median(ts[1:])
+        res["cases"][f"{regime}_filter_only(conf=1)"] = {"ms": round(ms, 4),
+                                                         "achieved_GBps": round(B * (4 + nc) * A * 4 / 1e9 / (ms / 1e3), 1),
+                                                         "hbm_frac": round(B * (4 + nc) * A * 4 / 1e9 / (ms / 1e3) / hbm, 4)}
+        del pred
+    torch.cuda.empty_cache()
+    return res
+
+
+def gpu_eager_baseline(local, batch):
+    """The honest GPU bar: the same architecture on stock PyTorch eager kernels (ATen / cuDNN conv, BN, SiLU
+    unfused like the reference; torchvision CUDA nms per image) on this B200, run in a SUBPROCESS (tools/
+    eager_gpu_baseline.py) after all of this repo's measurements, so no library kernel ever runs in the bench process."""
+    env = dict(os.environ)
+    vis = env.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = (vis.split(",")[local] if vis else str(local))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "eager_gpu_baseline.py"), str(batch)], env=env,
+                           capture_output=True, text=True, timeout=240)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": (r.stderr or r.stdout)[-300:]}
+        d = json.loads(line[-1])
+        d["what"] = ("reference architecture on stock PyTorch eager + cuDNN + torchvision CUDA nms on this GPU (subprocess); "
+                     "a reported GPU baseline, none of this repo's kernels")
+        return d
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     a = parse()
@@ -217,6 +364,12 @@ def main():
 
     torch.manual_seed(0)
     model = randomise_model_(DetectionModel(f"{model_name}.yaml", verbose=False)).eval()
+    n_sets = 3                                              # rotate inputs: 3 x 315 MB >> 126 MB L2
+    # identical in both arms (the driver compares it): what is computed, on which inputs, with which weights
+    config = {"workload": workload, "global_batch": a.batch * max(world, a.gpus if a.impl == "reference" else 1),
+              "inputs": f"synthetic torch.rand images; {n_sets} rotating batches of {a.batch * 3 * IMG * IMG * 4 / 1e6:.0f} MB "
+                        f"per GPU (> the 126 MB L2), so no timed step finds its input in cache",
+              "weights": "random init from cfg/yolo11.yaml, BN statistics randomised (seed 1)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -236,7 +389,7 @@ def main():
             "impl": "reference", "metric": "images_per_sec", "value": round(v, 3), "unit": "images/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(statistics.median(ts) * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": f"{sample_b} images/step of the bs={a.batch} workload"},
+            "config": config,
             "cpu_baseline": {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": "port",
                              "sample": f"oracle port (yolo11_ref fp32 unfused + nms_ref), {sample_b}-image steps x{steps}"},
             "e2e": {"value": round(v, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -262,7 +415,6 @@ def main():
     _C.init(dev)
     sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.to(dev)
-    n_sets = 3                                              # rotate inputs: 3 x 315 MB >> 126 MB L2
     host = [t.pin_memory() for t in synth_images(a.batch, n_sets, seed=rank)]
     devx = [t.to(dev) for t in host]
 
@@ -322,12 +474,16 @@ def main():
             run_steps(10, n_fly)
             torch.cuda.synchronize(dev)
         clk.mark()
-        ms_max, (dets, counts) = timed(a.steps, n_fly)
+        reps = []
+        for _ in range(max(1, a.repeats)):
+            ms_r, (dets, counts) = timed(a.steps, n_fly)
+            reps.append(ms_r)
+        ms_max = statistics.median(reps)
         ms_serial = ms_max
         if n_fly > 1:
-            ms_serial, _ = timed(a.steps, 1)
+            ms_serial = statistics.median([timed(a.steps, 1)[0] for _ in range(min(3, max(1, a.repeats)))])
         t_wait = time.perf_counter()
-        while clk.n_samples(since_mark=True) < 3 and time.perf_counter() - t_wait < 2.0:   # same load, untimed
+        while clk.n_samples(since_mark=True) < 10 and time.perf_counter() - t_wait < 2.0:   # same load, untimed
             run_steps(10, n_fly)
             torch.cuda.synchronize(dev)
     n_det_local = int(counts.sum().item())
@@ -349,7 +505,7 @@ def main():
                "unit": "ms", "what": f"{model_name} bs=1 640x640 device-resident input -> NMS'd count on host, 200 reps"}
 
     # ---- e2e through the public API, host tensors, H2D + D2H inside the timed region
-    e2e = None
+    e2e = e2e_half = e2e_u8 = h2d_ceiling = None
     if not a.no_e2e:
         from yololite import YOLOLite
 
@@ -357,47 +513,78 @@ def main():
         yl.model.load_state_dict(sd_cpu)
         yl.model.to(dev)
         kw = dict(conf=CONF, iou=IOU, max_det=MAX_DET, verbose=False, device=dev, batch=a.batch)
-        for i in range(3):
-            yl.predict(host[i % n_sets], **kw)
         steps_e = max(3, min(a.steps, 20))
-        barrier()
-        t0 = time.perf_counter()
-        nd = 0
-        prev = None
-        for i in range(steps_e):
-            res = yl.predict(host[i % n_sets], **kw)        # asynchronous: upload + kernels are only enqueued
-            if prev is not None:
-                nd += len(prev[0].boxes.data.cpu())         # device->host read of the PREVIOUS step's result
-            prev = res
-        nd += len(prev[0].boxes.data.cpu())
-        barrier()
-        dt = time.perf_counter() - t0
-        e2e = {"value": round(a.batch * world * steps_e / ydist.max_over_ranks(dt, dev), 1), "unit": "images/s",
-               "h2d_bytes_per_step": a.batch * 3 * IMG * IMG * 4, "d2h_bytes_per_step": a.batch * 4 + MAX_DET * 6 * 4,
-               "steps": steps_e, "api": "YOLOLite.predict(pinned host fp32 BCHW tensor); every step's Results are read on the host, one "
-                      "step behind the upload of the next batch (predict() is asynchronous, Results resolve lazily)"}
 
-    # ---- secondary e2e: the same API fed fp16 host tensors (the reference accepts them: `.float()` on the device,
-    # predictor.py:83): half the PCIe bytes, so the link stops being the bound
-    e2e_half = None
-    if not a.no_e2e:
+        def read_all(res):
+            """Device->host read of EVERY image's detections of a step: one batched copy of the padded (B, 300, 6)
+            detections + the (B,) counts (Results.batch.host()); returns the detection count and the bytes moved."""
+            d, c = res[0].batch.host()
+            return int(c.sum()), d.nbytes + c.nbytes
+
+        def e2e_run(host_batches, label):
+            for i in range(3):
+                read_all(yl.predict(host_batches[i % n_sets], **kw))
+            best = None
+            for _ in range(3):                                  # 3 x steps_e steps; the median run is reported
+                barrier()
+                t0 = time.perf_counter()
+                nd, d2h = 0, 0
+                prev = None
+                for i in range(steps_e):
+                    res = yl.predict(host_batches[i % n_sets], **kw)   # asynchronous: upload + kernels only enqueued
+                    if prev is not None:
+                        n_, b_ = read_all(prev)                 # D2H of the PREVIOUS step's results (all B images)
+                        nd += n_
+                        d2h = b_
+                    prev = res
+                n_, d2h = read_all(prev)
+                nd += n_
+                barrier()
+                dt = ydist.max_over_ranks(time.perf_counter() - t0, dev)
+                best = (best or []) + [dt]
+            dt = statistics.median(best)
+            hb = host_batches[0]
+            return {"value": round(a.batch * world * steps_e / dt, 1), "unit": "images/s",
+                    "h2d_bytes_per_step": hb.numel() * hb.element_size(), "d2h_bytes_per_step": d2h, "steps": steps_e,
+                    "runs_s": [round(t, 4) for t in best], "input": label, "detections": nd,
+                    "api": "YOLOLite.predict(pinned host BCHW tensor); EVERY image's detections of every step are read on the "
+                           "host (one batched D2H of dets + counts), one step behind the upload of the next batch "
+                           "(predict() is asynchronous, Results resolve lazily)"}
+
+        e2e = e2e_run(host, "pinned host fp32 BCHW tensor in [0, 1] (the reference arm's input)")
+        # secondary: the same API fed narrower host tensors — fp16 (the reference accepts it: `.float()` on the device,
+        # predictor.py:83) and uint8 image bytes (/255 on the device inside the fused stem; the reference's own uint8
+        # route is the numpy-image path, predictor.py:76-84): 2x / 4x fewer PCIe bytes, so the link stops being the bound
         host_h = [t.half().pin_memory() for t in host]
-        for i in range(3):
-            yl.predict(host_h[i % n_sets], **kw)
-        barrier()
-        t0 = time.perf_counter()
-        prev = None
-        for i in range(steps_e):
-            res = yl.predict(host_h[i % n_sets], **kw)
-            if prev is not None:
-                len(prev[0].boxes.data.cpu())
-            prev = res
-        len(prev[0].boxes.data.cpu())
-        barrier()
-        dt = time.perf_counter() - t0
-        e2e_half = {"value": round(a.batch * world * steps_e / ydist.max_over_ranks(dt, dev), 1), "unit": "images/s",
-                    "h2d_bytes_per_step": a.batch * 3 * IMG * IMG * 2, "input": "pinned host fp16 BCHW tensor"}
+        e2e_half = e2e_run(host_h, "pinned host fp16 BCHW tensor")
         del host_h
+        host_u8 = [(t * 255).round().to(torch.uint8).pin_memory() for t in host]
+        e2e_u8 = e2e_run(host_u8, "pinned host uint8 BCHW tensor (image bytes, /255 on the device)")
+        del host_u8
+
+        # ---- the box's pinned host->device ceiling at this rank count: the same bytes per step as the fp32 e2e, plain
+        # cudaMemcpyAsync on one stream per GPU, all ranks at once (max over ranks)
+        if not a.no_extras:
+            dst = torch.empty_like(devx[0])
+            cs = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(cs):
+                for i in range(3):
+                    dst.copy_(host[i % n_sets], non_blocking=True)
+            cs.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(cs):
+                for i in range(steps_e):
+                    dst.copy_(host[i % n_sets], non_blocking=True)
+            cs.synchronize()
+            dt = ydist.max_over_ranks(time.perf_counter() - t0, dev)
+            gbs = world * steps_e * dst.numel() * 4 / dt / 1e9
+            h2d_ceiling = {"aggregate_GBps": round(gbs, 1), "per_gpu_GBps": round(gbs / world, 1),
+                           "images_per_s_fp32": round(gbs * 1e9 / (3 * IMG * IMG * 4), 1),
+                           "e2e_frac_of_ceiling": round(e2e["value"] / (gbs * 1e9 / (3 * IMG * IMG * 4)), 3),
+                           "what": f"pinned host -> device cudaMemcpyAsync of {dst.numel() * 4 / 1e6:.0f} MB batches, one stream per "
+                                   f"GPU, {world} rank(s) concurrently, wall clock max over ranks"}
+            del dst
 
     # ---- image preprocess (SURVEY §8f rank 1): uint8 HWC BGR images -> letterboxed fp32 NCHW batch on the GPU
     prep = None
@@ -474,6 +661,24 @@ def main():
     n_det = int(gc.sum().item())
     assert n_det == ydist.sum_over_ranks(n_det_local, dev)
 
+    # ---- the other BASELINE configs, after every headline measurement (they free the headline's buffers first)
+    m256 = nms_stress = eager = None
+    if not a.no_extras:
+        if not a.no_e2e:
+            del yl
+        for k_ in [k_ for k_ in model.__dict__ if k_.startswith("_yl_")]:
+            del model.__dict__[k_]
+        del devx, host
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()
+        m256 = bench_yolo11m_sharded(dev, rank, world, dist, ydist)
+        if rank == 0:
+            nms_stress = bench_nms_stress(dev)
+        if dist is not None:
+            dist.barrier()
+        if rank == 0:
+            eager = gpu_eager_baseline(local, a.batch)
+
     cpu_b = None
     if rank == 0 and not a.no_cpu_baseline:
         if numa is not None:
@@ -493,12 +698,15 @@ def main():
             "in_flight": n_fly, "value_serial": round(total_images / (ms_serial / 1e3), 1),
             "bs1_latency_ms": lat,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "global_batch": a.batch * world, "parallelism": f"dp{world} batch-sharded, no collective",
-                       "cpu_affinity": (f"rank bound to the {len(numa[1])} cores NVML reports local to its GPU" if numa else "default"),
-                       "in_flight": f"{n_fly} batches in flight per GPU (one stream + one plan slot each)",
-                       "l2": f"{n_sets} rotating input batches of {a.batch * 3 * IMG * IMG * 4 / 1e6:.0f} MB each (> L2)",
-                       "weights": "random init from cfg/yolo11.yaml, BN statistics randomised (seed 1)"},
-            "clocks": clk.summary(), "e2e": e2e, "e2e_fp16_input": e2e_half, "gpu_launches": launches_per_step * a.steps,
+            "config": config,
+            "run": {"parallelism": f"dp{world} batch-sharded, no collective",
+                    "cpu_affinity": (f"rank bound to the {len(numa[1])} cores NVML reports local to its GPU" if numa else "default"),
+                    "in_flight": f"{n_fly} batches in flight per GPU (one stream + one plan slot each)"},
+            "repeats": {"n": len(reps), "ms_per_step_median": round(ms_max / a.steps, 4),
+                        "ms_per_step_min": round(min(reps) / a.steps, 4), "ms_per_step_max": round(max(reps) / a.steps, 4)},
+            "clocks": clk.summary(), "e2e": e2e, "e2e_fp16_input": e2e_half, "e2e_u8_input": e2e_u8,
+            "h2d_ceiling": h2d_ceiling, "yolo11m_bs256": m256, "nms_stress": nms_stress, "gpu_eager_baseline": eager,
+            "gpu_launches": launches_per_step * a.steps,
             "launches_per_step": launches_per_step, "detections_last_step": n_det,
             "roofline": roof, "preprocess": prep, "cpu_baseline": cpu_b, "kernel_breakdown": breakdown,
         }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define YL11_VERSION 102
+#define YL11_VERSION 200
 
 typedef enum yl_status {
     YL_OK = 0,
@@ -35,7 +35,8 @@ typedef enum yl_status {
     YL_ERR_NO_DEVICE = -5  /* no sm_100 device: the library has no CPU path    */
 } yl_status;
 
-typedef enum yl_dtype { YL_BF16 = 0, YL_F32 = 1 } yl_dtype;
+/* YL_U8 / YL_F16 are image-ingest types only (the caller's batch); activations are bf16, head outputs f32 */
+typedef enum yl_dtype { YL_BF16 = 0, YL_F32 = 1, YL_U8 = 2, YL_F16 = 3 } yl_dtype;
 typedef enum yl_act { YL_ACT_NONE = 0, YL_ACT_SILU = 1 } yl_act;
 typedef enum yl_conv_impl { YL_IMPL_AUTO = 0, YL_IMPL_DIRECT = 1, YL_IMPL_TCGEN05 = 2 } yl_conv_impl;
 
@@ -131,6 +132,18 @@ typedef struct yl_conv_args {
 int yl_conv_bn_act(const yl_conv_args* a, void* stream);
 /* 1 if the tcgen05 implicit-GEMM path can run this problem, 0 if it needs the direct kernel. */
 int yl_conv_tc_supported(const yl_conv_args* a);
+/* How the tcgen05 path would run this problem (the host-side dispatch of conv_tc.cu; nothing is launched): tests
+ * assert through it that the batch-size-dependent paths (image-stacked tiles, N split, halo patch, resident weights)
+ * are the ones a parity case exercised. */
+typedef struct yl_conv_tc_plan {
+    int flat;               /* 1x1: the (n,h,w) extent is one axis, tiles are 128 consecutive pixels */
+    int patch;              /* 3x3 s1 thin input: one halo-patch TMA box per tile, resident 9-tap weights */
+    int wres;               /* all weight tiles resident in shared memory (ring carries activations only) */
+    int tile_w, tile_h, tile_n;   /* A-tile box; tile_n > 1 = the same window of consecutive images stacked */
+    int m_tiles, n_tiles;   /* n_tiles == 2 with co <= 256: the wave-quantisation N split */
+    int co_tile, kblk, stages, grid, smem_bytes, tmem_cols;
+} yl_conv_tc_plan;
+int yl_conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out);
 
 /* First layer fused with the image ingest (predictor.py:81-84 + conv.py:35-53): reads the NCHW fp32 batch
  * (values rounded to bf16 like every other activation), 3x3 stride-2 pad-1 conv, <= 4 input channels, folded
@@ -188,18 +201,22 @@ int yl_xywh2xyxy_inplace(float* pred, int B, int C, int A, void* stream);
  * {gain, padx, pady, w0, h0}. */
 int yl_scale_boxes(float* dets, const int32_t* counts, int B, int max_det, const float* params_dev, void* stream);
 
-/* fp16 -> fp32 elementwise (n elements): ingest of half-precision image tensors, the `.float()` of
- * engine/predictor.py:83 when the caller hands over an fp16 batch (half the PCIe bytes of fp32). */
-int yl_f16_to_f32(const void* x_f16, float* y, long long n, void* stream);
+/* Elementwise widening of an image batch to fp32 (n elements): the `.float()` of engine/predictor.py:83 for fp16
+ * (x_dtype == YL_F16: half the PCIe bytes of fp32) and, for x_dtype == YL_U8, `.float() / 255` (the `/255` of
+ * predictor.py:84 / data/loaders.py:525-530; true fp32 division): a quarter of the PCIe bytes. */
+int yl_to_f32(const void* x, int x_dtype, float* y, long long n, void* stream);
 
 /* ---- fused stem --------------------------------------------------------------------------------------------- */
 /* Image ingest + layer 0 + layer 1 (cfg/yolo11.yaml:17-18: Conv(3,c0,3,2) -> Conv(c0,c1,3,2), each conv+BN+SiLU,
- * nn/modules/conv.py:47-49) in one kernel: reads the caller's NCHW fp32 batch once, keeps the layer-0 map in
+ * nn/modules/conv.py:47-49) in one kernel: reads the caller's NCHW batch once, keeps the layer-0 map in
  * shared memory (bf16, same rounding as the unfused path) and writes only the layer-1 output y (n, h/4, w/4, c1).
+ * x_dtype: YL_F32 (values used as they are), YL_F16 (widened), YL_U8 (image bytes: value / 255 in fp32, the
+ * predictor's `/255`): the narrow types cut the ingest's HBM read (and the caller's PCIe upload) 2x / 4x.
  * w0 / w1: yl_fold_bn_pack outputs.  yl_stem_fused_supported(ci, c0, c1): built for ci <= 3, c0 = 16, c1 = 32. */
 int yl_stem_fused_supported(int ci, int c0, int c1);
-int yl_stem_fused(const float* x_nchw, int n, int ci, int h, int w, const void* w0, int ci_pad0, const float* b0, int act0,
-                  const void* w1, int ci_pad1, const float* b1, int act1, const yl_tensor* y, void* stream);
+int yl_stem_fused(const void* x_nchw, int x_dtype, int n, int ci, int h, int w, const void* w0, int ci_pad0,
+                  const float* b0, int act0, const void* w1, int ci_pad1, const float* b1, int act1, const yl_tensor* y,
+                  void* stream);
 
 /* ---- fused C3k2 tail ----------------------------------------------------------------------------------------- */
 /* Everything after cv1 of a C3k2 / C2f block with ONE plain Bottleneck (nn/modules/block.py:231-235, 330-343,

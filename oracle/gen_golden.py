@@ -1,6 +1,6 @@
 """oracle/gen_golden.py — regenerate tests/golden/*.npz from the reference itself (build container only).
 
-    python oracle/gen_golden.py
+    python oracle/gen_golden.py --write [--only real scale_boxes ...]
 
 Fixtures (all seeded; weights are the name-keyed values of oracle/weights.py, so they are not stored):
   model_yolo11{n,s,m}.npz   reference DetectionModel forward on a (2,3,64,64) batch: y, raw head maps
@@ -15,9 +15,17 @@ Fixtures (all seeded; weights are the name-keyed values of oracle/weights.py, so
                             fp32 CPU output for it: the checkpoint-ingest fixture
   letterbox.npz             reference LetterBox (data/augment.py:612-681) + predictor.preprocess arithmetic
                             (engine/predictor.py:67-85) on seeded uint8 images (only seeds + outputs stored)
+  real_images.npz           BASELINE configs 1-2 on the reference's own fixtures with seeded weights (fp16-rounded, the
+                            reference pickles `.half()`): boats.jpg through YOLOLite.predict (auto letterbox 384x640, conf .25)
+                            and coco8 val through YOLOLite.val (rect batch 4x3x672x672, multi-label NMS conf .001):
+                            JPEG bytes + labels in, the reference's preprocessed batch (crc + sample), top-score rows of y,
+                            NMS output, scale_boxes'd detections, tp matrices and metrics out
+  scale_boxes.npz           reference ops.scale_boxes / clip_boxes (utils/ops.py:66-98,276-295) on seeded boxes, incl. the
+                            round(x - 0.1) pad and explicit ratio_pad
 """
 from __future__ import annotations
 
+import argparse
 import sys
 from pathlib import Path
 
@@ -30,6 +38,7 @@ from oracle.ref_harness import build_reference_model, import_reference  # noqa: 
 from oracle.weights import fill_state_dict_  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
+REF = "/root/reference"
 
 
 def seeded(shape, seed, lo=0.0, hi=1.0):
@@ -313,22 +322,206 @@ def gen_letterbox():
     print("letterbox.npz", len(LETTERBOX_CASES), "cases")
 
 
+REAL_TOPK = 384     # rows of y (anchors with the highest class score) kept per image
+
+
+def _capture_nms(ops_mod, store):
+    """Wrap the reference's ops.non_max_suppression (harness-side wrapper, the function itself is untouched): record the
+    pre-NMS tensor and the output, and lift the wall-clock bail-out (ops.py:207,269-271) that would truncate results."""
+    orig = ops_mod.non_max_suppression
+
+    def wrapped(prediction, *a, **kw):
+        p = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
+        store["y"] = p.detach().clone()
+        kw["max_time_img"] = 1e9
+        out = orig(prediction, *a, **kw)
+        store["nms"] = [o.detach().clone() for o in out]
+        return out
+
+    ops_mod.non_max_suppression = wrapped
+    return orig
+
+
+def _top_rows(y, k=REAL_TOPK):
+    """(B, 4+nc, A) -> indices (B, k) of the anchors with the highest max class score and their (B, 4+nc, k) columns."""
+    sc = y[:, 4:].amax(1)
+    idx = sc.argsort(dim=1, descending=True, stable=True)[:, :k]
+    return idx.numpy().astype(np.int32), torch.gather(y, 2, idx[:, None, :].expand(-1, y.shape[1], -1)).numpy()
+
+
+def gen_real_images():
+    import shutil
+    import tempfile
+    import zlib
+
+    import_reference()
+    import yaml
+    from yololite.data import dataset as ref_dataset
+    from yololite.engine import validator as ref_validator
+    from yololite.utils import ops as ref_ops
+
+    tmp = Path(tempfile.mkdtemp(prefix="ylref_real_"))
+    m = build_reference_model("n")
+    fill_state_dict_(m)
+    # the str-weights route is the one that works in the reference (SURVEY 0.5); it pickles / loads fp16 weights
+    torch.save({"model": m.half(), "train_args": {}, "ema": None}, tmp / "seeded.pt")
+    out = {"weights": np.array("oracle/weights.py fill_state_dict_(yolo11n), rounded to fp16 and back")}
+    cap = {}
+    orig_nms = _capture_nms(ref_ops, cap)
+
+    # ---- config 1: main.py:15 — YOLOLite(weights)(["boats.jpg"]) -> predictor, auto letterbox 384x640
+    boats = Path(REF) / "boats.jpg"
+    out["boats.jpg"] = np.frombuffer(boats.read_bytes(), dtype=np.uint8)
+    # YOLOLite.predict hands the in-memory module to AutoBackend, which crashes on the deleted `fuse` (SURVEY 0.5); the
+    # predictor it would construct (engine/model.py:95-99: conf .25, batch 1, mode predict) is built here with the
+    # weights as a path string, the route that works
+    from yololite.engine.predictor import DetectionPredictor
+
+    predictor = DetectionPredictor(overrides=dict(conf=0.25, batch=1, mode="predict", save=False, verbose=False,
+                                                  device="cpu", iou=0.7, project=str(tmp / "runs")))
+    res = predictor(source=[str(boats)], model=str(tmp / "seeded.pt"))
+    r = res[0]
+    y = cap["y"].float()
+    idx, cols = _top_rows(y)
+    out["boats.y_shape"] = np.array(y.shape)
+    out["boats.top_idx"], out["boats.top_cols"] = idx, cols
+    out["boats.nms"] = cap["nms"][0].numpy()            # letterboxed-image space (before scale_boxes)
+    out["boats.boxes"] = r.boxes.data.numpy()           # original-image space (after scale_boxes + clip)
+    out["boats.orig_shape"] = np.array(r.orig_shape)
+    print("boats", tuple(y.shape), "dets", len(r.boxes.data), "top score", float(y[:, 4:].max()))
+    # the predictor's preprocessed batch, recomputed with the reference's own LetterBox (what preprocess() ran)
+    import cv2
+    from yololite.data.augment import LetterBox
+
+    im0 = cv2.imread(str(boats))
+    lb = LetterBox((640, 640), auto=True, stride=32)(image=im0)
+    im = np.ascontiguousarray(np.stack([lb])[..., ::-1].transpose((0, 3, 1, 2)))
+    assert tuple(im.shape[2:]) == tuple(y.shape and (384, 640)), im.shape
+    out["boats.im_crc"] = np.array(zlib.crc32(im.tobytes()), dtype=np.int64)
+    out["boats.im_shape"] = np.array(im.shape)
+
+    # ---- config 2: YOLOLite.val on a scratch copy of coco8 (rect batch of 4, multi-label NMS, conf 0.001)
+    ds = tmp / "coco8"
+    shutil.copytree(Path(REF) / "coco8", ds, ignore=shutil.ignore_patterns("*.cache"))
+    cfg = yaml.safe_load((Path(REF) / "coco8" / "coco8.yaml").read_text())
+    cfg["path"] = str(ds)
+    (tmp / "coco8_abs.yaml").write_text(yaml.safe_dump(cfg))
+    # harness shim (SURVEY 0.5): cache_labels never writes "version" but get_labels pops it
+    orig_cache = ref_dataset.YOLODataset.cache_labels
+
+    def cache_labels(self, *a, **kw):
+        x = orig_cache(self, *a, **kw)
+        x["version"] = "harness"
+        return x
+
+    ref_dataset.YOLODataset.cache_labels = cache_labels
+    batches, stats_cap = [], {}
+    orig_update = ref_validator.DetectionValidator.update_metrics
+
+    def update_metrics(self, preds, batch):
+        batches.append({k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()})
+        stats_cap["predn"] = [self._prepare_pred(p, self._prepare_batch(si, batch)) for si, p in enumerate(preds)]
+        return orig_update(self, preds, batch)
+
+    ref_validator.DetectionValidator.update_metrics = update_metrics
+    orig_get_stats = ref_validator.DetectionValidator.get_stats
+
+    def get_stats(self):
+        stats_cap["stats"] = {k: torch.cat(v, 0).cpu().numpy() for k, v in self.stats.items()}
+        return orig_get_stats(self)
+
+    ref_validator.DetectionValidator.get_stats = get_stats
+    # engine/model.py:101-107: YOLOLite.val builds DetectionValidator(args={rect: True, mode: val, ...})(model=...)
+    validator = ref_validator.DetectionValidator(args=dict(rect=True, mode="val", data=str(tmp / "coco8_abs.yaml"),
+                                                           device="cpu", batch=16, workers=0, plots=False, verbose=False,
+                                                           project=str(tmp / "runs"), save_json=False))
+    validator(model=str(tmp / "seeded.pt"))
+    metrics = validator.metrics
+    assert len(batches) == 1
+    b = batches[0]
+    img = b["img"]                                      # validator.preprocess output: float /255 on the device
+    img_u8 = (img * 255).round().to(torch.uint8)
+    assert torch.equal(img_u8.float() / 255, img)
+    y = cap["y"].float()
+    idx, cols = _top_rows(y)
+    out["coco8.y_shape"] = np.array(y.shape)
+    out["coco8.top_idx"], out["coco8.top_cols"] = idx, cols
+    out["coco8.img_shape"] = np.array(img_u8.shape)
+    out["coco8.img_crc"] = np.array(zlib.crc32(img_u8.numpy().tobytes()), dtype=np.int64)
+    names = [Path(f).name for f in b["im_file"]]
+    out["coco8.files"] = np.array(names)
+    for i, f in enumerate(b["im_file"]):
+        out[f"coco8.jpg{i}"] = np.frombuffer(Path(f).read_bytes(), dtype=np.uint8)
+        lab = Path(f.replace("/images/", "/labels/", 1)).with_suffix(".txt")
+        out[f"coco8.txt{i}"] = np.array([r.split() for r in lab.read_text().strip().splitlines()], dtype=np.float32)
+    out["coco8.cls"] = b["cls"].numpy()
+    out["coco8.bboxes"] = b["bboxes"].numpy()
+    out["coco8.batch_idx"] = b["batch_idx"].numpy()
+    out["coco8.ori_shape"] = np.array(b["ori_shape"])
+    out["coco8.ratio"] = np.array([rp[0] for rp in b["ratio_pad"]], dtype=np.float64)
+    out["coco8.pad"] = np.array([rp[1] for rp in b["ratio_pad"]], dtype=np.float64)
+    nms = cap["nms"]
+    out["coco8.nms_counts"] = np.array([len(o) for o in nms])
+    out["coco8.nms"] = torch.cat(nms, 0).numpy()
+    out["coco8.predn"] = torch.cat(stats_cap["predn"], 0).numpy()
+    st = stats_cap["stats"]
+    out["coco8.tp"], out["coco8.conf"], out["coco8.pred_cls"] = st["tp"], st["conf"], st["pred_cls"]
+    out["coco8.target_cls"] = st["target_cls"]
+    rd = metrics.results_dict
+    out["coco8.metric_keys"] = np.array(list(rd.keys()))
+    out["coco8.metric_vals"] = np.array([float(v) for v in rd.values()], dtype=np.float64)
+    print("coco8", tuple(img_u8.shape), "nms counts", out["coco8.nms_counts"], "tp any", bool(st["tp"].any()), rd)
+    ref_ops.non_max_suppression = orig_nms
+    ref_dataset.YOLODataset.cache_labels = orig_cache
+    ref_validator.DetectionValidator.update_metrics = orig_update
+    ref_validator.DetectionValidator.get_stats = orig_get_stats
+    np.savez_compressed(GOLD / "real_images.npz", **out)
+    shutil.rmtree(tmp, ignore_errors=True)
+    print("real_images.npz", (GOLD / "real_images.npz").stat().st_size, "bytes")
+
+
+def gen_scale_boxes():
+    import_reference()
+    from yololite.utils import ops
+
+    g = np.random.default_rng(77)
+    cases = [  # (img1 (letterboxed) h,w ; img0 (original) h,w ; explicit ratio_pad or None)
+        ((384, 640), (1080, 1920), None), ((640, 640), (480, 640), None), ((640, 640), (427, 640), None),
+        ((672, 672), (428, 640), None), ((640, 480), (1080, 810), None), ((64, 64), (97, 131), None),
+        ((64, 96), (131, 97), None), ((640, 640), (333, 500), None), ((640, 640), (500, 333), None),
+        ((672, 672), (480, 640), ((1.05, 1.05), (0.0, 84.0))), ((672, 672), (640, 427), ((1.05, 1.05), (112.0, 0.0))),
+        ((640, 640), (1281, 1920), None),
+    ]
+    out = {"n_cases": np.array(len(cases))}
+    for i, (s1, s0, rp) in enumerate(cases):
+        n = 40
+        xy = g.uniform(-20, max(s1) + 20, (n, 2))
+        wh = g.uniform(1, 300, (n, 2))
+        boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        got = ops.scale_boxes(s1, torch.from_numpy(boxes.copy()), s0, ratio_pad=rp).numpy()
+        out[f"c{i}.img1"], out[f"c{i}.img0"] = np.array(s1), np.array(s0)
+        out[f"c{i}.ratio_pad"] = np.array([rp[0][0], rp[1][0], rp[1][1]] if rp else [0.0, 0.0, 0.0], dtype=np.float64)
+        out[f"c{i}.has_rp"] = np.array(rp is not None)
+        out[f"c{i}.boxes"], out[f"c{i}.out"] = boxes, got
+    np.savez_compressed(GOLD / "scale_boxes.npz", **out)
+    print("scale_boxes.npz", len(cases), "cases")
+
+
+GENERATORS = {
+    "val": lambda: gen_val_metrics(), "ckpt": lambda: gen_checkpoint(), "letterbox": lambda: gen_letterbox(),
+    "nms_torchvision": lambda: gen_nms_torchvision(), "nms_reference": lambda: gen_nms_reference(),
+    "modules": lambda: gen_modules(), "models": lambda: gen_models(), "real": lambda: gen_real_images(),
+    "scale_boxes": lambda: gen_scale_boxes(),
+}
+
 if __name__ == "__main__":
+    ap = argparse.ArgumentParser(description="Regenerate tests/golden/ from the unmodified reference in /root/reference")
+    ap.add_argument("--write", action="store_true", help="actually (over)write tests/golden/; without it nothing is touched")
+    ap.add_argument("--only", nargs="*", choices=sorted(GENERATORS), help="fixture groups to regenerate (default: all)")
+    args = ap.parse_args()
+    if not args.write:
+        ap.error("refusing to overwrite tests/golden/ without --write")
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    if "--only-letterbox" in sys.argv:
-        gen_letterbox()
-        sys.exit(0)
-    if "--only-ckpt" in sys.argv:
-        gen_checkpoint()
-        sys.exit(0)
-    if "--only-val" in sys.argv:
-        gen_val_metrics()
-        sys.exit(0)
-    gen_val_metrics()
-    gen_checkpoint()
-    gen_letterbox()
-    gen_nms_torchvision()
-    gen_nms_reference()
-    gen_modules()
-    gen_models()
+    for name in (args.only or list(GENERATORS)):
+        GENERATORS[name]()

@@ -17,6 +17,9 @@ REF_ROOT = "/root/reference"
 def import_reference():
     if not os.path.isdir(REF_ROOT):
         raise RuntimeError(f"{REF_ROOT} not present: the reference can only be imported in the build container")
+    cur = sys.modules.get("yololite")
+    if cur is not None and str(getattr(cur, "__file__", "")).startswith(REF_ROOT):
+        return cur                       # already the reference: keep module identities stable across calls
     os.environ.setdefault("YOLO_OFFLINE", "true")
     os.environ.setdefault("YOLO_AUTOINSTALL", "false")
     os.environ.setdefault("YOLO_CONFIG_DIR", tempfile.mkdtemp(prefix="ylref_cfg_"))

@@ -102,7 +102,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in yl11.h but not exported"
     assert declared == set(_C.EXPORTS)
-    assert _C.load().yl_version() == 102
+    assert _C.load().yl_version() == 200
 
 
 def test_no_gpu_fails_loudly():

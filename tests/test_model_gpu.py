@@ -296,3 +296,162 @@ def test_infer_nms_equals_infer_then_nms():
         d2, c2 = m.infer_nms(x, **kw)
         torch.cuda.synchronize()
         assert torch.equal(c1, c2)
+
+
+# ------------------------------------------------------------------------------------------------ benchmark shapes
+def _oracle_forward_chunked(sd, x, chunk=16):
+    from oracle import yolo11_ref
+
+    return torch.cat([yolo11_ref.forward(sd, x[i:i + chunk])[0] for i in range(0, x.shape[0], chunk)], 0)
+
+
+def test_model_bs64_matches_oracle_with_batch_dependent_dispatch(golden):
+    """The benchmark's own shape (BASELINE config 3: yolo11n, 640x640, bs=64): conv dispatch that depends on the batch
+    size — image-stacked 128-row tiles on the 20x20 maps, the wave-quantisation N split (148 < m_tiles <= 296), the halo-patch
+    and resident-weight modes — is asserted to be taken, the head output is within tolerance of the fp32 oracle on all
+    64 images and the NMS (both label modes) is bit-exact against the oracle on the same pre-NMS tensor."""
+    from oracle import nms_ref
+    from yololite.nn.tasks import DetectionModel
+
+    g = golden("model_yolo11n.npz")
+    sd = model_state_dict(g)
+    m = DetectionModel("yolo11n.yaml", verbose=False)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.rand(64, 3, 640, 640, generator=torch.Generator().manual_seed(3))
+    xc = x.cuda()
+    y, _ = m.infer(xc)
+    assert tuple(y.shape) == (64, 84, 8400)
+    plan = m._get_plan(xc.shape, xc.device)[0]
+    disp = plan.conv_dispatch()
+    assert len(disp) >= 40
+    stacked = [d for d, i in disp if i.tile_n > 1]
+    nsplit = [d for d, i in disp if i.n_tiles == 2 and i.co_tile <= 128]
+    patch = [d for d, i in disp if i.patch]
+    wres = [d for d, i in disp if i.wres]
+    assert any("20x20" in d for d in stacked), "image-stacked tiles were not used on the 20x20 maps"
+    assert nsplit and all("20x20" in d for d in nsplit), f"N split not taken at bs=64: {nsplit}"
+    assert patch and wres, (patch, wres)
+    yr = _oracle_forward_chunked(sd, x).numpy()
+    yc = y.cpu().numpy()
+    assert np.abs(yc[:, :4] - yr[:, :4]).max() <= BOX_TOL_PX
+    assert np.abs(yc[:, 4:] - yr[:, 4:]).max() <= SCORE_TOL
+    # the whole step as the bench runs it (model + NMS in one plan / CUDA graph), against the oracle NMS on the SAME tensor
+    for kw, multi in ((dict(conf_thres=0.25, iou_thres=0.7), False), (dict(conf_thres=0.001, iou_thres=0.7, multi_label=True), True)):
+        dets, counts = m.infer_nms(xc, kw["conf_thres"], kw["iou_thres"], None, False, multi, 300)
+        dets, counts = dets.cpu().numpy(), counts.cpu().numpy()
+        ref = nms_ref.non_max_suppression(yc, max_det=300, **kw)
+        assert list(counts) == [len(r) for r in ref]
+        for i, r in enumerate(ref):
+            np.testing.assert_array_equal(dets[i, : counts[i]], r, err_msg=f"image {i} multi={multi}")
+
+
+@pytest.mark.parametrize("scale", ["s", "m"])
+def test_model_s_m_640_match_oracle(golden, scale):
+    """yolo11s / yolo11m at the benchmark resolution (640x640: K up to 4608, two N tiles, M = 1600 / 6400 per image),
+    B = 2: head output within tolerance of the fp32 oracle, NMS bit-exact on the same tensor."""
+    from oracle import nms_ref, yolo11_ref
+    from yololite.nn.tasks import DetectionModel
+    from yololite.utils import ops
+
+    g = golden(f"model_yolo11{scale}.npz")
+    sd = model_state_dict(g)
+    m = DetectionModel(f"yolo11{scale}.yaml", verbose=False)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.rand(2, 3, 640, 640, generator=torch.Generator().manual_seed(5))
+    yr, _ = yolo11_ref.forward(sd, x)
+    y, _ = m.infer(x.cuda())
+    yc = y.cpu().numpy()
+    assert np.abs(yc[:, :4] - yr.numpy()[:, :4]).max() <= BOX_TOL_PX
+    assert np.abs(yc[:, 4:] - yr.numpy()[:, 4:]).max() <= SCORE_TOL
+    got = ops.non_max_suppression(y.clone(), conf_thres=0.05, iou_thres=0.7)
+    ref = nms_ref.non_max_suppression(yc, conf_thres=0.05, iou_thres=0.7)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+
+
+# ------------------------------------------------------------------------------------------------ narrow ingest
+@pytest.mark.parametrize("scale,hw", [("n", (64, 96)), ("n", (640, 640)), ("s", (64, 64))])
+def test_uint8_and_fp16_ingest_equal_the_widened_fp32_batch(golden, scale, hw):
+    """A uint8 image batch (bytes, /255 on ingest: predictor.py:83-84) and an fp16 batch give bit-identical outputs to
+    the same values widened to fp32 first: inside the fused stem for yolo11n (no widened copy ever exists), through
+    one conversion launch for the other scales."""
+    from yololite import _C
+    from yololite.nn.tasks import DetectionModel
+
+    g = golden(f"model_yolo11{scale}.npz")
+    m = DetectionModel(f"yolo11{scale}.yaml", verbose=False)
+    m.load_state_dict(model_state_dict(g))
+    m = m.cuda().eval()
+    gen = torch.Generator().manual_seed(11)
+    xu = torch.randint(0, 256, (3, 3, *hw), dtype=torch.uint8, generator=gen).cuda()
+    y_ref = m.infer(xu.float() / 255)[0].clone()
+    y_u8 = m.infer(xu)[0].clone()
+    assert torch.equal(y_u8, y_ref)
+    plan = m._get_plan(xu.shape, xu.device)[0]
+    assert (_C.YL_U8 in plan.native_ingest) == (scale == "n")
+    xh = (xu.float() / 255).half()
+    assert torch.equal(m.infer(xh)[0], m.infer(xh.float())[0].clone())
+    # a non-contiguous / unaligned uint8 batch takes the generic path and still means "bytes / 255"
+    xs = torch.randint(0, 256, (3, 3, hw[0], hw[1] + 32), dtype=torch.uint8, generator=gen).cuda()[..., 16:16 + hw[1]]
+    assert not xs.is_contiguous()
+    assert torch.equal(m.infer(xs)[0].clone(), m.infer(xs.contiguous().float() / 255)[0])
+
+
+def test_predict_uint8_host_tensor_matches_fp32_path():
+    """A pinned uint8 host batch (a quarter of the fp32 upload) through the chunk-pipelined predictor gives exactly the
+    detections of the same images fed as fp32 / 255."""
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    xu = torch.randint(0, 256, (32, 3, 64, 64), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).pin_memory()
+    kw = dict(imgsz=64, conf=0.001, verbose=False, device=0, batch=32)
+    r8 = yl.predict(xu, **kw)
+    assert yl.predictor._chunking(xu) == 4
+    r32 = yl.predict((xu.float() / 255).pin_memory(), **kw)
+    assert len(r8) == len(r32) == 32
+    for a, b in zip(r8, r32):
+        assert np.array_equal(a.boxes.data.cpu().numpy(), b.boxes.data.cpu().numpy())
+    assert np.asarray(r8[0].orig_img).dtype == np.uint8 and np.asarray(r8[0].orig_img).shape == (64, 64, 3)
+
+
+def test_predict_alternating_batch_shapes_and_plan_cache_bound():
+    """(a) a full host batch followed by a partial one (and back) must not corrupt the earlier, still
+    unread Results: staging states are kept per shape and side streams are drained before anything is freed;
+    (b) the per-model plan cache is bounded (LRU) however many shapes / NMS settings stream through."""
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    g = torch.Generator().manual_seed(9)
+    full = torch.rand(32, 3, 64, 64, generator=g).pin_memory()
+    part = torch.rand(16, 3, 64, 64, generator=g).pin_memory()
+    odd = torch.rand(16, 3, 96, 64, generator=g).pin_memory()
+    kw = dict(imgsz=64, conf=0.001, verbose=False, device=0)
+    want = {id(t): [r.boxes.data.cpu().numpy() for r in yl.predict(t, batch=len(t), **kw)] for t in (full, part)}
+    want[id(odd)] = [r.boxes.data.cpu().numpy() for r in yl.predict(odd, batch=16, imgsz=(96, 64), conf=0.001, verbose=False, device=0)]
+    for _ in range(3):
+        pending = []
+        for t in (full, part, odd, part, full):     # more shapes than pipeline_states slots would keep at 2
+            kk = dict(kw, imgsz=(96, 64)) if t is odd else kw
+            pending.append((t, yl.predict(t, batch=len(t), **kk)))      # asynchronous; read only afterwards
+        for t, res in pending[-2:]:                  # the documented pattern: batch k-1 is read after submitting k
+            for r, w in zip(res, want[id(t)]):
+                assert np.array_equal(r.boxes.data.cpu().numpy(), w)
+    model = yl.model
+    model.max_plans = 4
+    x = torch.rand(1, 3, 64, 64).cuda()
+    for i in range(12):
+        model.infer_nms(x, conf=0.01 + 0.01 * i, iou=0.7)
+    assert len(model.__dict__["_yl_plans"]) <= 4
+    d, c = model.infer_nms(x, conf=0.01, iou=0.7)    # evicted long ago: rebuilt, still correct
+    y, _ = model.infer(x)
+    from yololite.utils import ops
+
+    d0, c0 = ops.nms_padded(y.clone(), 0.01, 0.7, None, False, False, 300)
+    assert torch.equal(c, c0) and torch.equal(d[0, : int(c[0])], d0[0, : int(c0[0])])
+    assert len(model.infer_nms(x, conf=0.3, iou=0.5, classes=0)) == 2          # an int `classes` is legal

@@ -127,6 +127,38 @@ def test_nms_stress_properties_full_size(ops):
         np.testing.assert_array_equal(d[i, : c[i]], ref[j])
 
 
+@pytest.mark.parametrize("multi_label", [False, True])
+def test_nms_stress_dense_full_size_vs_oracle(ops, multi_label):
+    """BASELINE config 5, DENSE regime at full size (B=256, A=8400, nc=80, conf=0.001): every anchor is a candidate
+    (8400 per image; multi-label expands to > 30000 pairs per image, i.e. the max_nms sort-and-cut path, ops.py:254-255).
+    32 images spread over the batch are compared bit-for-bit with the oracle."""
+    from oracle import nms_ref
+
+    B = 256
+    g = torch.Generator(device="cuda").manual_seed(2)
+    pred = torch.empty((B, 84, 8400), device="cuda")
+    pred[:, 0:2] = torch.rand((B, 2, 8400), device="cuda", generator=g) * 640
+    pred[:, 2:4] = torch.rand((B, 2, 8400), device="cuda", generator=g) * 248 + 8
+    pred[:, 4:] = torch.sigmoid(torch.randn((B, 80, 8400), device="cuda", generator=g) * 2.0 - 5.0)
+    k = 8400 // 3                               # clusters of near-duplicate boxes so that suppression happens
+    src = torch.randint(0, 8400, (k,), device="cuda", generator=g)
+    pred[:, 0:4, :k] = pred[:, 0:4, src] + torch.randn((B, 4, k), device="cuda", generator=g) * 1.5
+    ncand = (pred[:, 4:].amax(1) > 0.001).sum(1)
+    assert int(ncand.min()) >= 8300                                             # dense: (almost) every anchor passes
+    if multi_label:
+        assert int((pred[:, 4:] > 0.001).sum((1, 2)).min()) > 30000            # the max_nms path is taken
+    dets, counts = ops.nms_batched(pred, 0.001, 0.7, multi_label=multi_label, max_det=300)
+    torch.cuda.synchronize()
+    c, d = counts.cpu().numpy(), dets.cpu().numpy()
+    assert (c == 300).all()
+    idx = list(range(0, B, 8))
+    assert len(idx) == 32
+    ref = nms_ref.non_max_suppression(pred[idx].cpu().numpy(), conf_thres=0.001, iou_thres=0.7, multi_label=multi_label,
+                                      max_det=300)
+    for j, i in enumerate(idx):
+        np.testing.assert_array_equal(d[i, : c[i]], ref[j], err_msg=f"image {i}")
+
+
 def test_nms_argument_errors(ops):
     from yololite import _C
 

@@ -7,6 +7,7 @@ namespace yl {
 bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len);
 int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream);
 int launch_conv_direct(const yl_conv_args* a, cudaStream_t stream);
+int conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out);
 }  // namespace yl
 
 extern "C" {
@@ -14,6 +15,11 @@ extern "C" {
 int yl_conv_tc_supported(const yl_conv_args* a) {
     if (!a) return 0;
     return yl::conv_tc_supported(a, nullptr, 0) ? 1 : 0;
+}
+
+int yl_conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out) {
+    YL_CHECK(a != nullptr && out != nullptr, YL_ERR_ARG, "null argument");
+    return yl::conv_tc_info(a, out);
 }
 
 int yl_conv_bn_act(const yl_conv_args* a, void* stream) {

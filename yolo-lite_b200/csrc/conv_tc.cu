@@ -727,7 +727,9 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
+// Everything of a launch that is decided on the host: tiling, mode (flat / halo patch / resident weights / N split),
+// smem carve-up and the tensor maps.  Shared by the launch and by yl_conv_tc_info (tests assert which path ran).
+static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* smem_out) {
     char why[128];
     YL_CHECK(conv_tc_supported(a, why, sizeof(why)), YL_ERR_UNSUPPORTED, "tcgen05 conv unsupported: %s", why);
     const yl_tensor& x = a->x;
@@ -743,7 +745,6 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
                  "y_up dims mismatch: got (%d,%d,%d) expected (%d,%d,%d)", a->y_up.n, a->y_up.h, a->y_up.w, x.n, 2 * Ho,
                  2 * Wo);
 
-    ConvTcParams p;
     memset(&p, 0, sizeof(p));
     p.ksize = a->k;
     p.stride = a->stride;
@@ -970,11 +971,45 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     p.res_coff = a->res.coff;
     p.res_c = a->res.c;
 
-    if (g_dbg_buf && g_dbg_next < g_dbg_cap) p.dbg = g_dbg_buf + 16ll * g_dbg_next++;
     int grid = g_num_sms * (ctas_per_sm < env_int("YL_GRID_CTAS", 2) ? ctas_per_sm : env_int("YL_GRID_CTAS", 2));
     if (grid > p.total_tiles) grid = p.total_tiles;
+    *grid_out = grid;
+    *smem_out = smem;
+    return YL_OK;
+}
+
+int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
+    ConvTcParams p;
+    int grid = 0;
+    size_t smem = 0;
+    const int rc = plan_conv_tc(a, p, &grid, &smem);
+    if (rc != YL_OK) return rc;
+    if (g_dbg_buf && g_dbg_next < g_dbg_cap) p.dbg = g_dbg_buf + 16ll * g_dbg_next++;
     YL_CUDA(launch_kernel(conv_tc_kernel, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
     YL_LAUNCH_OK("conv_tc_kernel");
+    return YL_OK;
+}
+
+int conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out) {
+    ConvTcParams p;
+    int grid = 0;
+    size_t smem = 0;
+    const int rc = plan_conv_tc(a, p, &grid, &smem);
+    if (rc != YL_OK) return rc;
+    out->flat = (p.Ho == 1 && p.Nimg == 1 && p.TW == 128 && !p.patch) ? 1 : 0;
+    out->patch = p.patch;
+    out->wres = p.wres;
+    out->tile_w = p.TW;
+    out->tile_h = p.TH;
+    out->tile_n = p.TN;
+    out->m_tiles = p.m_tiles;
+    out->n_tiles = p.n_tiles;
+    out->co_tile = p.co_tile;
+    out->kblk = p.kblk;
+    out->stages = p.stages;
+    out->grid = grid;
+    out->smem_bytes = (int)smem;
+    out->tmem_cols = (int)p.tmem_cols;
     return YL_OK;
 }
 

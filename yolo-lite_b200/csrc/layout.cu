@@ -103,20 +103,44 @@ __global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restric
     }
 }
 
+// uint8 image bytes -> fp32 in [0, 1]: float(b) / 255 with a true (round-to-nearest) division, 16 bytes per thread
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long long n16,
+                                                        long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float4* o = reinterpret_cast<float4*>(y) + 4 * i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = make_float4(__fdiv_rn((float)(w[k] & 0xffu), 255.f), __fdiv_rn((float)((w[k] >> 8) & 0xffu), 255.f),
+                               __fdiv_rn((float)((w[k] >> 16) & 0xffu), 255.f), __fdiv_rn((float)(w[k] >> 24), 255.f));
+    } else if (i == n16) {
+        for (long long j = n16 * 16; j < n; ++j) y[j] = __fdiv_rn((float)x[j], 255.f);
+    }
+}
+
 static bool aligned8(const yl_tensor* t) { return t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; }
 
 }  // namespace yl
 
 extern "C" {
 
-int yl_f16_to_f32(const void* x_f16, float* y, long long n, void* stream) {
-    YL_CHECK(x_f16 && y && n >= 0, YL_ERR_ARG, "bad f16_to_f32 arguments");
-    YL_CHECK(((uintptr_t)x_f16 | (uintptr_t)y) % 16 == 0, YL_ERR_ARG, "f16_to_f32 needs 16-byte aligned pointers");
+int yl_to_f32(const void* x, int x_dtype, float* y, long long n, void* stream) {
+    YL_CHECK(x && y && n >= 0, YL_ERR_ARG, "bad to_f32 arguments");
+    YL_CHECK(x_dtype == YL_F16 || x_dtype == YL_U8, YL_ERR_ARG, "to_f32 converts YL_F16 or YL_U8 (got dtype %d)", x_dtype);
+    YL_CHECK(((uintptr_t)x | (uintptr_t)y) % 16 == 0, YL_ERR_ARG, "to_f32 needs 16-byte aligned pointers");
     if (n == 0) return YL_OK;
-    const long long n8 = n / 8;
-    yl::f16_to_f32_kernel<<<(unsigned)yl::ceil_div64(n8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(x_f16), y, n8, n);
-    YL_LAUNCH_OK("f16_to_f32_kernel");
+    if (x_dtype == YL_F16) {
+        const long long n8 = n / 8;
+        yl::f16_to_f32_kernel<<<(unsigned)yl::ceil_div64(n8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const __half*>(x), y, n8, n);
+    } else {
+        const long long n16 = n / 16;
+        yl::u8_to_f32_kernel<<<(unsigned)yl::ceil_div64(n16 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint8_t*>(x), y, n16, n);
+    }
+    YL_LAUNCH_OK("to_f32_kernel");
     return YL_OK;
 }
 

@@ -17,12 +17,14 @@
 //   stage 2  layer 1: warp = output row, 9 taps = 9 k-steps of 16 channels, 4 n-tiles; bias + SiLU; 4x4 quad
 //            transposes so each lane stores 16 B (64 contiguous bytes per pixel)
 // Persistent grid over tiles; weights / biases staged once per CTA before the PDL dependency wait.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace yl {
 
 struct StemFusedParams {
-    const float* x;               // (N, CI, H, W) fp32
+    const void* x;                // (N, CI, H, W) fp32 | fp16 | uint8 (image bytes, /255)
     int N, CI, H, W;
     const __nv_bfloat16* w0;      // [16][9 * ci_pad0]
     int ci_pad0;
@@ -49,6 +51,39 @@ __device__ __forceinline__ void sf_mma(float (&d)[4], const uint32_t (&a)[4], ui
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Four consecutive pixels of one channel plane, as loaded (16 / 8 / 4 bytes) and widened to fp32.  uint8 is the
+// predictor's image-byte path: float(b) / 255 in fp32 with a true division (predictor.py:84), then the same bf16
+// rounding as every other activation.
+template <typename T> struct SfQuad;
+template <> struct SfQuad<float> {
+    using raw = float4;
+    static __device__ __forceinline__ raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ raw load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ float4 widen(raw v) { return v; }
+    static __device__ __forceinline__ float one(const float* p) { return __ldg(p); }
+};
+template <> struct SfQuad<__half> {
+    using raw = uint2;
+    static __device__ __forceinline__ raw zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ raw load(const __half* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+    static __device__ __forceinline__ float4 widen(raw v) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ float one(const __half* p) { return __half2float(*p); }
+};
+template <> struct SfQuad<uint8_t> {
+    using raw = uint32_t;
+    static __device__ __forceinline__ raw zero() { return 0u; }
+    static __device__ __forceinline__ raw load(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    static __device__ __forceinline__ float4 widen(raw v) {
+        return make_float4(__fdiv_rn((float)(v & 0xffu), 255.f), __fdiv_rn((float)((v >> 8) & 0xffu), 255.f),
+                           __fdiv_rn((float)((v >> 16) & 0xffu), 255.f), __fdiv_rn((float)(v >> 24), 255.f));
+    }
+    static __device__ __forceinline__ float one(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.f); }
+};
+
 constexpr int SF_TH = 8, SF_TW = 16;                 // layer-1 output tile
 constexpr int SF_R0 = 2 * SF_TH + 1, SF_C0 = 2 * SF_TW + 1;   // 17 x 33 layer-0 pixels
 constexpr int SF_RI = 2 * SF_R0 + 1;                 // 35 input rows
@@ -64,7 +99,10 @@ constexpr int SF_OFF_B = SF_OFF_W1 + 32 * SF_W1S;                  // b0[16], b1
 constexpr int SF_OFF_TAB = SF_OFF_B + 48 * 4;                      // uint2 [36 m-tiles][16 rows]: stage-1 geometry
 constexpr int SF_SMEM = SF_OFF_TAB + SF_M0 * 16 * 8;
 
+template <typename TIn>
 __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParams p) {
+    using Q = SfQuad<TIn>;
+    const TIn* px_in = reinterpret_cast<const TIn*>(p.x);
     extern __shared__ __align__(16) uint8_t sf_smem[];
     griddep_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,11 +168,11 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
     griddep_wait();
 
     const long long plane = (long long)p.H * p.W;
-    const bool vec_ok = (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    const bool vec_ok = (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & (4 * sizeof(TIn) - 1)) == 0);
     constexpr int QUADS = SF_CI / 4;
     constexpr int ITEMS = SF_RI * QUADS;                       // 630 quads of 4 pixels
     constexpr int ROUNDS = (ITEMS + 255) / 256;
-    float4 pf[ROUNDS][3];                                      // the next tile's patch, in flight across stage 2
+    typename Q::raw pf[ROUNDS][3];                             // the next tile's patch, in flight across stage 2
 
     // Stage 0 is split in two so that its HBM round trip hides behind stage 2 of the previous tile: `patch_issue`
     // only issues the loads (quads are 16-byte aligned in the image, so with W % 4 == 0 each one is entirely inside
@@ -144,18 +182,18 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
         const int oh0 = ((tile / p.tiles_w) % p.tiles_h) * SF_TH;
         const int n = tile / (p.tiles_w * p.tiles_h);
         const int ir0 = 4 * oh0 - 3, ic0 = 4 * ow0 - 4;   // input coords of patch (0, 0)
-        const float* xn = p.x + (long long)n * p.CI * plane;
+        const TIn* xn = px_in + (long long)n * p.CI * plane;
 #pragma unroll
         for (int j = 0; j < ROUNDS; ++j) {
             const int item = threadIdx.x + j * 256;
             const int pr = item / QUADS, q = item - pr * QUADS;
             const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
             const bool ok = item < ITEMS && hi >= 0 && hi < p.H && wi0 >= 0 && wi0 < p.W;
-            const float* src0 = xn + (long long)(ok ? hi : 0) * p.W + (ok ? wi0 : 0);
+            const TIn* src0 = xn + (long long)(ok ? hi : 0) * p.W + (ok ? wi0 : 0);
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                pf[j][ci] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && ci < p.CI) pf[j][ci] = __ldg(reinterpret_cast<const float4*>(src0 + ci * plane));
+                pf[j][ci] = Q::zero();
+                if (ok && ci < p.CI) pf[j][ci] = Q::load(src0 + ci * plane);
             }
         }
     };
@@ -166,10 +204,9 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
             if (item >= ITEMS) continue;
             const int pr = item / QUADS, q = item - pr * QUADS;
             uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
-            dst[0] = make_uint4(pack_bf16x2(pf[j][0].x, pf[j][1].x), pack_bf16x2(pf[j][2].x, 0.f),
-                                pack_bf16x2(pf[j][0].y, pf[j][1].y), pack_bf16x2(pf[j][2].y, 0.f));
-            dst[1] = make_uint4(pack_bf16x2(pf[j][0].z, pf[j][1].z), pack_bf16x2(pf[j][2].z, 0.f),
-                                pack_bf16x2(pf[j][0].w, pf[j][1].w), pack_bf16x2(pf[j][2].w, 0.f));
+            const float4 c0 = Q::widen(pf[j][0]), c1 = Q::widen(pf[j][1]), c2 = Q::widen(pf[j][2]);
+            dst[0] = make_uint4(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f), pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f));
+            dst[1] = make_uint4(pack_bf16x2(c0.z, c1.z), pack_bf16x2(c2.z, 0.f), pack_bf16x2(c0.w, c1.w), pack_bf16x2(c2.w, 0.f));
         }
     };
     // general shapes (W % 4 != 0 or an unaligned base): element-wise, synchronous
@@ -178,7 +215,7 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
         const int oh0 = ((tile / p.tiles_w) % p.tiles_h) * SF_TH;
         const int n = tile / (p.tiles_w * p.tiles_h);
         const int ir0 = 4 * oh0 - 3, ic0 = 4 * ow0 - 4;
-        const float* xn = p.x + (long long)n * p.CI * plane;
+        const TIn* xn = px_in + (long long)n * p.CI * plane;
         for (int item = threadIdx.x; item < ITEMS; item += blockDim.x) {
             const int pr = item / QUADS, q = item - pr * QUADS;
             const int hi = ir0 + pr, wi0 = ic0 + 4 * q;
@@ -189,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) stem_fused_kernel(const StemFusedParam
                 for (int e = 0; e < 4; ++e) {
                     v[ci][e] = 0.f;
                     if (ci < p.CI && hi >= 0 && hi < p.H && wi0 + e >= 0 && wi0 + e < p.W)
-                        v[ci][e] = __ldg(xn + ci * plane + (long long)hi * p.W + wi0 + e);
+                        v[ci][e] = Q::one(xn + ci * plane + (long long)hi * p.W + wi0 + e);
                 }
             uint4* dst = reinterpret_cast<uint4*>(s_in + pr * SF_CI + 4 * q);
             dst[0] = make_uint4(pack_bf16x2(v[0][0], v[1][0]), pack_bf16x2(v[2][0], 0.f), pack_bf16x2(v[0][1], v[1][1]),
@@ -342,7 +379,9 @@ int init_stem_fused() {
     int dev = 0;
     YL_CUDA(cudaGetDevice(&dev));
     YL_CUDA(cudaDeviceGetAttribute(&g_sf_sms, cudaDevAttrMultiProcessorCount, dev));
-    YL_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    YL_CUDA(cudaFuncSetAttribute(stem_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    YL_CUDA(cudaFuncSetAttribute(stem_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    YL_CUDA(cudaFuncSetAttribute(stem_fused_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
     return YL_OK;
 }
 
@@ -350,10 +389,12 @@ int init_stem_fused() {
 
 extern "C" int yl_stem_fused_supported(int ci, int c0, int c1) { return ci >= 1 && ci <= 3 && c0 == 16 && c1 == 32; }
 
-extern "C" int yl_stem_fused(const float* x_nchw, int n, int ci, int h, int w, const void* w0, int ci_pad0, const float* b0,
-                             int act0, const void* w1, int ci_pad1, const float* b1, int act1, const yl_tensor* y,
-                             void* stream) {
+extern "C" int yl_stem_fused(const void* x_nchw, int x_dtype, int n, int ci, int h, int w, const void* w0, int ci_pad0,
+                             const float* b0, int act0, const void* w1, int ci_pad1, const float* b1, int act1,
+                             const yl_tensor* y, void* stream) {
     YL_CHECK(x_nchw && w0 && b0 && w1 && b1 && y && y->data, YL_ERR_ARG, "null pointer");
+    YL_CHECK(x_dtype == YL_F32 || x_dtype == YL_F16 || x_dtype == YL_U8, YL_ERR_ARG,
+             "fused stem reads fp32, fp16 or uint8 images (got dtype %d)", x_dtype);
     YL_CHECK(y->dtype == YL_BF16, YL_ERR_ARG, "stem output must be bf16");
     YL_CHECK(yl_stem_fused_supported(ci, 16, y->c) && ci_pad1 == 16, YL_ERR_UNSUPPORTED,
              "fused stem is built for <= 3 input channels, 16 -> 32 (got ci = %d, c1 = %d, ci_pad1 = %d)", ci, y->c, ci_pad1);
@@ -392,7 +433,12 @@ extern "C" int yl_stem_fused(const float* x_nchw, int n, int ci, int h, int w, c
     per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
     int grid = sms * per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
-    YL_CUDA(yl::launch_kernel(yl::stem_fused_kernel, dim3(grid), dim3(256), (size_t)yl::SF_SMEM, (cudaStream_t)stream, p));
+    if (x_dtype == YL_F32)
+        YL_CUDA(yl::launch_kernel(yl::stem_fused_kernel<float>, dim3(grid), dim3(256), (size_t)yl::SF_SMEM, (cudaStream_t)stream, p));
+    else if (x_dtype == YL_F16)
+        YL_CUDA(yl::launch_kernel(yl::stem_fused_kernel<__half>, dim3(grid), dim3(256), (size_t)yl::SF_SMEM, (cudaStream_t)stream, p));
+    else
+        YL_CUDA(yl::launch_kernel(yl::stem_fused_kernel<uint8_t>, dim3(grid), dim3(256), (size_t)yl::SF_SMEM, (cudaStream_t)stream, p));
     YL_LAUNCH_OK("stem_fused_kernel");
     return YL_OK;
 }

@@ -15,7 +15,9 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libyl11.so"
 _lib = None
 _inited_devices: set[int] = set()
 
-YL_BF16, YL_F32 = 0, 1
+YL_BF16, YL_F32, YL_U8, YL_F16 = 0, 1, 2, 3
+#: torch dtypes an image batch may arrive in -> yl_dtype (uint8 = image bytes, scaled by 1/255 on ingest)
+INGEST_DTYPES = {torch.float32: YL_F32, torch.float16: YL_F16, torch.uint8: YL_U8}
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
 
@@ -93,6 +95,13 @@ class ConvArgs(C.Structure):
     ]
 
 
+class ConvTcPlan(C.Structure):
+    """Mirror of `yl_conv_tc_plan` (how the tcgen05 path would run a conv; yl_conv_tc_info)."""
+
+    _fields_ = [(k, C.c_int32) for k in ("flat", "patch", "wres", "tile_w", "tile_h", "tile_n", "m_tiles", "n_tiles",
+                                         "co_tile", "kblk", "stages", "grid", "smem_bytes", "tmem_cols")]
+
+
 _PROTOTYPES = {
     "yl_version": (C.c_int, []),
     "yl_last_error_string": (C.c_char_p, []),
@@ -106,6 +115,7 @@ _PROTOTYPES = {
     "yl_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "yl_conv_bn_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "yl_conv_tc_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "yl_conv_tc_info": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvTcPlan)]),
     "yl_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                C.POINTER(Tensor), C.c_int, C.c_void_p]),
     "yl_dwconv3x3": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_int,
@@ -125,9 +135,9 @@ _PROTOTYPES = {
                                C.c_void_p, C.c_void_p]),
     "yl_xywh2xyxy_inplace": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "yl_scale_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "yl_f16_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "yl_to_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
     "yl_stem_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "yl_stem_fused": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+    "yl_stem_fused": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(Tensor), C.c_void_p]),
     "yl_c3k2_tail_supported": (C.c_int, [C.c_int, C.c_int]),
     "yl_c3k2_tail": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -5,6 +5,9 @@ import torch
 
 from . import _plan
 
+#: plans kept per standalone module (LRU over input shapes)
+MAX_MODULE_PLANS = 8
+
 
 def _as_f32_cuda(t: torch.Tensor) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or t.dim() != 4:
@@ -22,7 +25,12 @@ def run_standalone(module, x):
     key = (tuple(tuple(t.shape) for t in xs), dev.index)
     plans = module.__dict__.setdefault("_yl_plans", {})
     entry = plans.get(key)
-    if entry is None:
+    if entry is not None:
+        plans[key] = plans.pop(key)
+    else:
+        if len(plans) >= MAX_MODULE_PLANS:          # LRU: see BaseModel._get_plan
+            torch.cuda.synchronize(dev)
+            plans.pop(next(iter(plans)))
         with torch.cuda.device(dev):
             g = _plan.Builder(dev)
             statics = [torch.empty(tuple(t.shape), dtype=torch.float32, device=dev) for t in xs]

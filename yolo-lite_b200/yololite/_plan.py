@@ -216,7 +216,7 @@ class Builder:
         h1, w1 = (h0 - 1) // 2 + 1, (w0 - 1) // 2 + 1
         y = self._out(out, x.n, h1, w1, pc1.co)
         yt = y.ct()
-        self._push(self.lib.yl_stem_fused, x.static.data_ptr(), x.n, x.c, x.h, x.w, pc0.w.data_ptr(), pc0.ci_pad,
+        self._push(self.lib.yl_stem_fused, x.static.data_ptr(), _C.YL_F32, x.n, x.c, x.h, x.w, pc0.w.data_ptr(), pc0.ci_pad,
                    pc0.bias.data_ptr(), int(act0), pc1.w.data_ptr(), pc1.ci_pad, pc1.bias.data_ptr(), int(act1),
                    C.byref(yt), keep=(yt, pc0, pc1, x.static), kind="stem_fused",
                    bytes_=x.n * x.c * x.h * x.w * 4 + x.n * h1 * w1 * pc1.co * 2,
@@ -328,15 +328,32 @@ class Plan:
         self._skip = 0
         self.n_launches = len(b.calls)
 
-    def run(self, ingest_ptr: int | None = None):
-        """Replay.  `ingest_ptr`: device pointer of an NCHW fp32 batch to read instead of the static input
-        (only the first call, the image ingest, consumes it; it is never part of the CUDA graph)."""
+    @property
+    def native_ingest(self):
+        """yl_dtypes the plan's first launch reads directly from the caller's batch: the fused stem takes fp32, fp16
+        and uint8 images; the other ingests (stem_conv, nchw_to_nhwc) read fp32 only."""
+        if not self.calls:
+            return ()
+        name = self.calls[0][0].__name__
+        if name == "yl_stem_fused":
+            return (_C.YL_F32, _C.YL_F16, _C.YL_U8)
+        return (_C.YL_F32,) if name in ("yl_nchw_to_nhwc", "yl_stem_conv") else ()
+
+    def run(self, ingest_ptr: int | None = None, ingest_dtype: int = _C.YL_F32):
+        """Replay.  `ingest_ptr`: device pointer of an NCHW batch (of `ingest_dtype`, one of `native_ingest`) to read
+        instead of the static input (only the first call, the image ingest, consumes it; it is never part of the CUDA
+        graph)."""
         s = _C.stream_ptr()
         first = 0
         if self.graph is not None or ingest_ptr is not None:
             for fn, args, _ in self.calls[: self._skip if self.graph is not None else 1]:
-                a = (ingest_ptr,) + tuple(args[1:]) if (ingest_ptr is not None and
-                                                         fn.__name__ in ("yl_nchw_to_nhwc", "yl_stem_conv", "yl_stem_fused")) else args
+                a = args
+                if ingest_ptr is not None and fn.__name__ in ("yl_nchw_to_nhwc", "yl_stem_conv", "yl_stem_fused"):
+                    if fn.__name__ == "yl_stem_fused":
+                        a = (ingest_ptr, int(ingest_dtype)) + tuple(args[2:])
+                    else:
+                        assert ingest_dtype == _C.YL_F32, "this plan's ingest kernel reads fp32 only"
+                        a = (ingest_ptr,) + tuple(args[1:])
                 _C.check(fn(*a, s), fn.__name__)
             first = self._skip if self.graph is not None else 1
         if self.graph is not None:
@@ -351,6 +368,19 @@ class Plan:
             rc = fn(*args, s)
             if rc != 0:
                 check(rc, fn.__name__)
+
+    def conv_dispatch(self):
+        """[(meta desc, _C.ConvTcPlan)] for every tcgen05 conv launch of the plan: which host-side dispatch (image-stacked
+        tiles, N split, halo patch, resident weights) each one takes at THIS batch size (yl_conv_tc_info)."""
+        lib = _C.load()
+        out = []
+        for (fn, args, _), md in zip(self.calls, self.meta):
+            if md["kind"] != "conv_tc":
+                continue
+            info = _C.ConvTcPlan()
+            _C.check(lib.yl_conv_tc_info(args[0], C.byref(info)), "yl_conv_tc_info")
+            out.append((md["desc"], info))
+        return out
 
     def time_launches(self, reps: int = 3, inner: int = 4):
         """Per-launch device time (ms, median of `reps` eager passes in plan order) via CUDA events on the

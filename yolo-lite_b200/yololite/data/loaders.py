@@ -15,7 +15,17 @@ IMG_FORMATS = {"bmp", "dng", "jpeg", "jpg", "mpo", "png", "tif", "tiff", "webp",
 
 
 class LoadTensor:
-    """A BCHW float tensor in [0, 1] (values > 1 are taken as 0-255 and rescaled, like the reference)."""
+    """A BCHW image tensor (reference data/loaders.py:480-548).
+
+    * float32 / float16: values in [0, 1], used as they are.
+    * uint8: image bytes 0..255; the model's ingest kernel divides by 255 on the device (the reference crashes on a
+      uint8 tensor — `torch.finfo(uint8)`, loaders.py:525 — so this is an extension: 4x fewer PCIe / HBM bytes).
+    * The reference also accepts a FLOAT tensor holding 0..255 values: `im.max() > 1 + eps` -> warning + `/255`
+      (loaders.py:525-530).  That check is a full pass over the batch on the host (more expensive than the whole
+      GPU pipeline for a 64-image batch), so it is opt-in here: `LoadTensor.check_range = True` restores it."""
+
+    #: run the reference's `im.max() > 1` range check (and rescale by 1/255) on float tensors
+    check_range = False
 
     def __init__(self, im0: torch.Tensor, stride=32):
         if im0.dim() == 3:
@@ -23,6 +33,12 @@ class LoadTensor:
         if im0.dim() != 4 or im0.shape[2] % stride or im0.shape[3] % stride:
             raise ValueError(f"torch.Tensor inputs should be BCHW i.e. shape(1, 3, 640, 640) divisible by stride "
                              f"{stride}. Input shape{tuple(im0.shape)} is incompatible.")
+        if self.check_range and im0.is_floating_point() and im0.max() > 1.0 + torch.finfo(im0.dtype).eps:
+            import warnings
+
+            warnings.warn(f"torch.Tensor inputs should be normalized 0.0-1.0 but max value is {float(im0.max())}. "
+                          f"Dividing input by 255.")
+            im0 = im0.float() / 255.0
         self.im0 = im0
         self.bs = im0.shape[0]
         self.mode = "image"

@@ -34,7 +34,8 @@ class _LazyTensorImage:
         self.shape = (batch.shape[2], batch.shape[3], batch.shape[1])
 
     def __array__(self, dtype=None, copy=None):
-        a = (self._b[self._i].permute(1, 2, 0) * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
+        im = self._b[self._i].permute(1, 2, 0)
+        a = (im if im.dtype == torch.uint8 else (im.float() * 255).clamp(0, 255).to(torch.uint8)).cpu().numpy()
         return a.astype(dtype) if dtype is not None else a
 
 
@@ -69,7 +70,9 @@ class DetectionPredictor:
         float, /255 as ONE CUDA kernel over the raw bytes (bit-exact against the reference's cv2 path): the upload
         is the uint8 pixels, 4x fewer PCIe bytes than the fp32 batch of the reference (predictor.py:67-85)."""
         if isinstance(im, torch.Tensor):
-            return im.to(self.device, non_blocking=True).float()
+            im = im.to(self.device, non_blocking=True)
+            # uint8 = image bytes: kept narrow, the model's ingest divides by 255 on the fly (yl_stem_fused / yl_to_f32)
+            return im if im.dtype in (torch.uint8, torch.float16, torch.float32) else im.float()
         same_shapes = len({x.shape for x in im}) == 1
         if all(isinstance(x, np.ndarray) and x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 3 for x in im):
             from ..data.augment import _Staging, letterbox_batch_cuda
@@ -93,11 +96,13 @@ class DetectionPredictor:
     #: chunks in flight on the GPU (1 or 2): consecutive chunks alternate between two streams / plan slots, so
     #: the launch-latency-bound small layers of one chunk overlap the bandwidth-bound layers of the other
     in_flight = 2
+    #: staging states (device staging batches + output buffers) kept per backend, LRU over (shape, max_det, dtype)
+    pipeline_states = 3
 
     def _chunking(self, im):
         """Number of ingest chunks for a host tensor batch (1 = plain path)."""
         if not isinstance(im, torch.Tensor) or im.is_cuda or im.dim() != 4 \
-                or im.dtype not in (torch.float32, torch.float16) or not im.is_contiguous():
+                or im.dtype not in (torch.float32, torch.float16, torch.uint8) or not im.is_contiguous():
             return 1
         b = im.shape[0]
         for n in range(int(self.pipeline_chunks), 1, -1):
@@ -112,22 +117,38 @@ class DetectionPredictor:
         dev = self.device
         B = im_host.shape[0]
         cb = B // n_chunks
-        half = im_host.dtype == torch.float16     # half the PCIe bytes; widened on the device (predictor.py:83 `.float()`)
-        key = (tuple(im_host.shape), a.max_det, half)
+        # fp16 / uint8 batches stay narrow all the way into the model's ingest kernel (2x / 4x fewer PCIe and HBM bytes);
+        # uint8 means image bytes and is scaled by 1/255 there (reference predictor.py:83-84: `.float()`, `/= 255`)
+        key = (tuple(im_host.shape), a.max_det, str(im_host.dtype))
         # the staging state lives on the backend: YOLOLite.predict builds a fresh predictor per call, but the pinned
-        # upload pipeline (two device staging batches, streams, events) must survive across calls
-        st = self.model.__dict__.get("_yl_pipe_state")
-        if st is None or st["key"] != key:
-            st = {"key": key, "bufs": [torch.empty(im_host.shape, dtype=torch.float32, device=dev) for _ in range(2)],
-                  "raw": [torch.empty(im_host.shape, dtype=torch.float16, device=dev) for _ in range(2)] if half else None,
+        # upload pipeline (two device staging batches, streams, events) must survive across calls.  The side streams
+        # are shared by every state; buffers are kept per (shape, max_det, dtype) in a small LRU so that alternating
+        # batch shapes (a full batch followed by the last partial one) neither reallocate nor free memory that
+        # launches still in flight on the side streams are using.
+        pipe = self.model.__dict__.get("_yl_pipe")
+        if pipe is None:
+            pipe = self.model.__dict__["_yl_pipe"] = {
+                "copy": torch.cuda.Stream(device=dev), "lanes": [torch.cuda.Stream(device=dev) for _ in range(2)],
+                "post": torch.cuda.Stream(device=dev), "states": {}, "snap": None}
+        states = pipe["states"]
+        st = states.get(key)
+        if st is not None:
+            states[key] = states.pop(key)                # most recently used last
+        else:
+            if len(states) >= self.pipeline_states:
+                # the evicted buffers were only ever used on the side streams: drain those before the allocator may
+                # hand the blocks to somebody else (the caller's stream never touched them)
+                for side in (pipe["copy"], *pipe["lanes"], pipe["post"]):
+                    side.synchronize()
+                states.pop(next(iter(states)))
+            st = {"key": key, "bufs": [torch.empty(im_host.shape, dtype=im_host.dtype, device=dev) for _ in range(2)],
                   "free": [None, None], "turn": 0,
                   "dets": torch.empty((B, a.max_det, 6), dtype=torch.float32, device=dev),
                   "counts": torch.empty((B,), dtype=torch.int32, device=dev),
-                  "copy": torch.cuda.Stream(device=dev),
-                  "lanes": [torch.cuda.Stream(device=dev) for _ in range(2)],
-                  "post": torch.cuda.Stream(device=dev), "snap": None,
                   "events": [torch.cuda.Event() for _ in range(n_chunks)]}
-            self.model.__dict__["_yl_pipe_state"] = st
+            states[key] = st
+        st["copy"], st["lanes"], st["post"] = pipe["copy"], pipe["lanes"], pipe["post"]
+        self.model.__dict__["_yl_pipe_state"] = st       # the state the most recent call used
         j = st["turn"]
         st["turn"] ^= 1
         buf = st["bufs"][j]
@@ -144,26 +165,20 @@ class DetectionPredictor:
         main = torch.cuda.current_stream(dev)
         for side in (st["copy"], *st["lanes"]):
             side.wait_stream(main)
-        land = st["raw"][j] if half else buf      # where the upload lands
         with torch.cuda.stream(st["copy"]):
             for k in range(n_chunks):
-                land[k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
+                buf[k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
                 st["events"][k].record(st["copy"])
         model = self.model.model
-        lib = _C.load()
         fly = max(1, min(int(self.in_flight), n_chunks, 2))
         lanes = st["lanes"][:fly]
         for ln in lanes:
-            if st.get("snap") is not None:
-                ln.wait_event(st["snap"])        # the previous call's snapshot of dets / counts has been taken
+            if pipe["snap"] is not None:
+                ln.wait_event(pipe["snap"])      # the previous call's snapshot of dets / counts has been taken
         for k in range(n_chunks):
             ln = lanes[k % fly]
             with torch.cuda.stream(ln):
                 ln.wait_event(st["events"][k])
-                if half:
-                    src, dstc = land[k * cb:(k + 1) * cb], buf[k * cb:(k + 1) * cb]
-                    _C.check(lib.yl_f16_to_f32(src.data_ptr(), dstc.data_ptr(), dstc.numel(), _C.stream_ptr()),
-                             "yl_f16_to_f32")
                 # model + NMS of the chunk are one CUDA-graph launch; its plan-owned outputs are gathered into the
                 # batch-level buffers (115 KB per 16 images)
                 d, c = model.infer_nms(buf[k * cb:(k + 1) * cb], a.conf, a.iou, a.classes, a.agnostic_nms, False,
@@ -183,9 +198,9 @@ class DetectionPredictor:
         if stream is not None:
             with torch.cuda.stream(stream):
                 results = self.postprocess(preds, img, orig_imgs, nms_out=nms_out)
-            st = self.model.__dict__.get("_yl_pipe_state")
-            if st is not None:
-                st["snap"] = results[0]._lazy[0].ready if results and results[0]._lazy else None
+            pipe = self.model.__dict__.get("_yl_pipe")
+            if pipe is not None:
+                pipe["snap"] = results[0]._lazy[0].ready if results and results[0]._lazy else None
             return results
         a = self.args
         if nms_out is None:
@@ -258,10 +273,10 @@ class DetectionPredictor:
                     with profilers[2]:
                         self.results = self.postprocess(None, im, im0s, nms_out=(dets, counts), stream=post)
                 else:
-                    st = self.model.__dict__.get("_yl_pipe_state")
-                    if st is not None:     # an asynchronous host-tensor batch may still own the plan slots
+                    pipe = self.model.__dict__.get("_yl_pipe")
+                    if pipe is not None:   # an asynchronous host-tensor batch may still own the plan slots
                         cur = torch.cuda.current_stream(self.device)
-                        for side in (*st["lanes"], st["post"]):
+                        for side in (*pipe["lanes"], pipe["post"]):
                             cur.wait_stream(side)
                     with profilers[0]:
                         im = self.preprocess(im0s)

@@ -103,6 +103,22 @@ class BatchDetections:
     def boxes(self, i: int) -> torch.Tensor:
         return self.dets[i, : self.n()[i]]
 
+    def host(self):
+        """(dets (B, max_det, 6) float32, counts (B,) int32) as numpy arrays: the whole batch's detections in ONE
+        device->host copy per tensor (rows beyond counts[i] are padding).  Cached."""
+        if getattr(self, "_host", None) is None:
+            cur = torch.cuda.current_stream(self.dets.device)
+            cur.wait_event(self.ready)
+            self.dets.record_stream(cur)
+            self.counts.record_stream(cur)
+            d = self.dets.to("cpu", non_blocking=True)
+            c = self.counts.to("cpu", non_blocking=True)
+            cur.synchronize()
+            self._host = (d.numpy(), c.numpy())
+            if self._n is None:
+                self._n = self._host[1].tolist()
+        return self._host
+
 
 class Results:
     def __init__(self, orig_img, path, names, boxes=None, speed=None, lazy=None):
@@ -111,6 +127,7 @@ class Results:
         self.orig_shape = orig_img.shape[:2] if orig_img is not None else None
         self._boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
         self._lazy = lazy
+        self._batch = lazy[0] if lazy is not None else None
         self.masks = self.probs = self.keypoints = self.obb = None
         self.speed = speed or {"preprocess": None, "inference": None, "postprocess": None}
         self.names = names
@@ -128,6 +145,12 @@ class Results:
     @boxes.setter
     def boxes(self, value):
         self._boxes, self._lazy = value, None
+
+    @property
+    def batch(self):
+        """The device-resident detections of the whole batch this result belongs to (`BatchDetections`: `.host()` reads
+        all of them with one copy), or None for results constructed from explicit boxes."""
+        return self._batch
 
     def __len__(self):
         return len(self.boxes) if self.boxes is not None else 0

@@ -29,6 +29,12 @@ class YLModule(nn.Module):
 
     # -- cache hygiene ---------------------------------------------------------------------------------
     def _yl_invalidate(self):
+        """Drop every cached plan / packed weight / pipeline state.  Their buffers may still be in use by launches in
+        flight on side streams (asynchronous predict), and freeing them would let the caching allocator reuse the
+        memory under those launches: drain the device first."""
+        if torch.cuda.is_available() and torch.cuda.is_initialized() and any(
+                k.startswith("_yl_") for m in self.modules() for k in m.__dict__):
+            torch.cuda.synchronize()
         for m in self.modules():
             for k in [k for k in m.__dict__ if k.startswith("_yl_")]:
                 del m.__dict__[k]

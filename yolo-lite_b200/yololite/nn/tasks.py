@@ -149,6 +149,9 @@ class BaseModel(YLModule):
 
     #: capture each plan into a CUDA graph (one launch per forward); set False to debug launch by launch
     use_cuda_graph = True
+    #: plans kept per model (LRU): every (shape, slot, NMS arguments) owns activation buffers + a CUDA graph, so a
+    #: stream of differently shaped rect batches or a conf/iou sweep must not grow GPU memory without bound
+    max_plans = 16
     #: return fresh tensors from forward() like the reference; engine code uses infer() and skips the copy
     clone_outputs = True
 
@@ -333,7 +336,14 @@ class BaseModel(YLModule):
         plans = self.__dict__.setdefault("_yl_plans", {})
         key = (tuple(shape), dev.index, bool(self.use_cuda_graph), bool(want_raw), int(slot), nms)
         entry = plans.get(key)
-        if entry is None:
+        if entry is not None:
+            plans[key] = plans.pop(key)                     # most recently used last (dicts keep insertion order)
+        else:
+            if len(plans) >= max(int(self.max_plans), 1):
+                # evict the least recently used plan; its buffers / graph may still be in flight on some stream, and the
+                # caching allocator would hand them to the new plan: drain the device first (rare, build-time cost)
+                torch.cuda.synchronize(dev)
+                plans.pop(next(iter(plans)))
             with torch.cuda.device(dev):
                 g = _plan.Builder(dev)
                 g.want_raw = bool(want_raw)   # Detect writes its raw (B, H, W, no) maps only on request
@@ -373,13 +383,29 @@ class BaseModel(YLModule):
         if x.shape[2] % s or x.shape[3] % s:
             raise ValueError(f"image size {tuple(x.shape[2:])} must be a multiple of the model stride {s}")
         plan, static_in, y, raws = self._get_plan(x.shape, dev, want_raw, slot)
-        with torch.cuda.device(dev):
-            if x.dtype == torch.float32 and x.is_contiguous():
-                plan.run(ingest_ptr=x.data_ptr())          # zero-copy: the ingest kernel reads x directly
-            else:
-                static_in.copy_(x, non_blocking=True)
-                plan.run()
+        self._run_plan(plan, static_in, x, dev)
         return y, raws
+
+    @staticmethod
+    def _run_plan(plan, static_in, x, dev):
+        """Feed `x` to the plan's ingest.  fp32 is read in place (zero-copy); fp16 is widened and uint8 is taken as
+        image bytes (value / 255, the predictor's `/255`, predictor.py:84) — inside the fused stem when the plan has one,
+        otherwise by one conversion launch into the plan's static fp32 input."""
+        from .. import _C
+
+        with torch.cuda.device(dev):
+            yd = _C.INGEST_DTYPES.get(x.dtype)
+            if yd is not None and x.is_contiguous() and yd in plan.native_ingest and x.data_ptr() % 16 == 0:
+                plan.run(ingest_ptr=x.data_ptr(), ingest_dtype=yd)
+            elif yd in (_C.YL_F16, _C.YL_U8) and x.is_contiguous() and x.data_ptr() % 16 == 0:
+                _C.check(_C.load().yl_to_f32(x.data_ptr(), yd, static_in.data_ptr(), x.numel(), _C.stream_ptr()), "yl_to_f32")
+                plan.run()
+            else:
+                if x.dtype == torch.uint8:
+                    static_in.copy_(x.float() / 255, non_blocking=True)
+                else:
+                    static_in.copy_(x, non_blocking=True)
+                plan.run()
 
     @torch.no_grad()
     def infer_nms(self, x: torch.Tensor, conf=0.25, iou=0.45, classes=None, agnostic=False, multi_label=False,
@@ -394,15 +420,12 @@ class BaseModel(YLModule):
         s = int(self.stride.max()) if hasattr(self, "stride") else 32
         if x.shape[2] % s or x.shape[3] % s:
             raise ValueError(f"image size {tuple(x.shape[2:])} must be a multiple of the model stride {s}")
+        if classes is not None and not isinstance(classes, (list, tuple)):
+            classes = [classes] if isinstance(classes, int) else list(classes)      # `classes=0` is legal in the reference
         nms = (float(conf), float(iou), None if classes is None else tuple(int(c) for c in classes), bool(agnostic),
                bool(multi_label), int(max_det), int(max_nms), float(max_wh))
         plan, static_in, _, post = self._get_plan(x.shape, dev, False, slot, nms)
-        with torch.cuda.device(dev):
-            if x.dtype == torch.float32 and x.is_contiguous():
-                plan.run(ingest_ptr=x.data_ptr())
-            else:
-                static_in.copy_(x, non_blocking=True)
-                plan.run()
+        self._run_plan(plan, static_in, x, dev)
         return post
 
     def fuse(self, verbose=True):
