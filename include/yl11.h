@@ -100,8 +100,14 @@ int yl_upsample2x(const yl_tensor* x, const yl_tensor* y, void* stream);
  *   mode YL_DET_BOX  (co == 4*reg_max, reg_max == 16): DFL softmax-expectation per side (block.py:51-69),
  *        dist2bbox around the anchor centre (tal.py:341-350), * stride  -> pred[b, 0:4, anchor0 + a_local]
  *   mode YL_DET_CLS  (co == nc): sigmoid                               -> pred[b, 4:4+nc, anchor0 + a_local]
+ *   mode YL_DET_CLS_FILTER (co == nc): sigmoid, best class per anchor and the confidence test of
+ *        ops.non_max_suppression (utils/ops.py:203, 242-244: `conf, j = cls.max(1)`, strict `conf > conf_thres`, ties
+ *        keep the lowest class index), all in the conv epilogue: every passing anchor becomes one candidate key in
+ *        the NMS workspace `cand_ws` (layout of yl_nms_workspace_bytes(B, A, nc, 0), counters zeroed by
+ *        yl_nms_begin), exactly the key yl_nms_batched's filter kernel would emit from the stored scores.  The class
+ *        rows of pred are then never written (nor re-read): yl_nms_select finishes the step.  Single-label NMS only.
  * With det.pred != NULL the NHWC destination `y` becomes optional (y.data may be NULL: no raw map at all). */
-typedef enum yl_det_mode { YL_DET_NONE = 0, YL_DET_BOX = 1, YL_DET_CLS = 2 } yl_det_mode;
+typedef enum yl_det_mode { YL_DET_NONE = 0, YL_DET_BOX = 1, YL_DET_CLS = 2, YL_DET_CLS_FILTER = 3 } yl_det_mode;
 typedef struct yl_det_epilogue {
     float* pred;     /* NULL: plain conv epilogue */
     int32_t mode;    /* yl_det_mode */
@@ -110,6 +116,9 @@ typedef struct yl_det_epilogue {
     int32_t A;       /* anchors per image over all levels */
     int32_t anchor0; /* first anchor of this level */
     float stride;    /* level stride in pixels */
+    float conf;      /* YL_DET_CLS_FILTER: confidence threshold */
+    int32_t _pad;
+    void* cand_ws;   /* YL_DET_CLS_FILTER: NMS workspace receiving the candidates */
 } yl_det_epilogue;
 
 typedef struct yl_conv_args {
@@ -191,6 +200,13 @@ int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, do
                    int32_t* counts, void* stream);
 /* torchvision.ops.nms semantics on explicit boxes (n,4) xyxy + scores (n): keep (int64[n]) gets the kept
  * indices in descending score order, *count their number.  workspace >= yl_nms_boxes_workspace_bytes(n). */
+/* The two halves of yl_nms_batched for a step whose class filter runs inside the Detect head convs
+ * (YL_DET_CLS_FILTER): yl_nms_begin zeroes the per-image candidate counters of `workspace` (before those convs),
+ * yl_nms_select runs the per-image sort + greedy suppression on the candidates found there.  `pred` needs valid box
+ * rows only.  Same outputs, bit for bit, as yl_nms_batched(multi_label = 0, classes = NULL) on the full tensor. */
+int yl_nms_begin(void* workspace, size_t workspace_bytes, int B, void* stream);
+int yl_nms_select(const float* pred, int B, int nc, int A, double iou_thres, int agnostic, int max_det, int max_nms,
+                  float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* counts, void* stream);
 size_t yl_nms_boxes_workspace_bytes(int n);
 int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thres, void* workspace,
                  size_t workspace_bytes, int64_t* keep, int32_t* count, void* stream);

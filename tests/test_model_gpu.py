@@ -208,7 +208,15 @@ def test_fused_decode_matches_decode_kernel_and_engine_path(golden):
     assert np.abs(yf[:, 4:] - yk[:, 4:]).max() <= 1e-5
 
 
-def test_predict_pipelined_host_batch_equals_device_batch(golden):
+@pytest.fixture
+def chunk_small_batches(monkeypatch):
+    """Let the small test batches take the chunk-pipelined ingest (by default only >= 48 MB chunks are split off)."""
+    from yololite.engine.predictor import DetectionPredictor
+
+    monkeypatch.setattr(DetectionPredictor, "pipeline_min_chunk_bytes", 0)
+
+
+def test_predict_pipelined_host_batch_equals_device_batch(golden, chunk_small_batches):
     """A pinned HOST batch goes through the chunk-pipelined ingest (4 chunks of 8); the detections must be the
     same as for the same batch already resident on the device (single plan, no chunking)."""
     from oracle.weights import fill_state_dict_
@@ -289,6 +297,13 @@ def test_infer_nms_equals_infer_then_nms():
         d1, c1 = m.infer_nms(x, **kw)
         torch.cuda.synchronize()
         assert torch.equal(c0, c1), kw
+        # single-label without a class list: the confidence filter runs inside the head convs (no filter kernel, no
+        # class-score rows); everything else takes the two-kernel NMS on the full prediction
+        key = (float(kw["conf"]), float(kw["iou"]), None if kw.get("classes") is None else tuple(kw["classes"]),
+               bool(kw.get("agnostic", False)), bool(kw.get("multi_label", False)), int(kw.get("max_det", 300)), 30000, 7680.0)
+        kinds = [md["kind"] for md in m._get_plan(x.shape, x.device, False, 0, key)[0].meta]
+        fused = not kw.get("multi_label", False) and kw.get("classes") is None
+        assert ("nms_select" in kinds and "nms_begin" in kinds and "nms" not in kinds) == fused, (kw, kinds[-4:])
         n = c0.tolist()
         for i in range(3):
             assert np.array_equal(d0[i, : n[i]].cpu().numpy(), d1[i, : n[i]].cpu().numpy()), (kw, i)
@@ -326,11 +341,11 @@ def test_model_bs64_matches_oracle_with_batch_dependent_dispatch(golden):
     disp = plan.conv_dispatch()
     assert len(disp) >= 40
     stacked = [d for d, i in disp if i.tile_n > 1]
-    nsplit = [d for d, i in disp if i.n_tiles == 2 and i.co_tile <= 128]
+    nsplit = [(d, i.m_tiles) for d, i in disp if i.n_tiles == 2 and i.co_tile <= 128]
     patch = [d for d, i in disp if i.patch]
     wres = [d for d, i in disp if i.wres]
     assert any("20x20" in d for d in stacked), "image-stacked tiles were not used on the 20x20 maps"
-    assert nsplit and all("20x20" in d for d in nsplit), f"N split not taken at bs=64: {nsplit}"
+    assert len(nsplit) >= 8 and all(148 < mt <= 296 for _, mt in nsplit), f"N split not taken at bs=64: {nsplit}"
     assert patch and wres, (patch, wres)
     yr = _oracle_forward_chunked(sd, x).numpy()
     yc = y.cpu().numpy()
@@ -399,7 +414,7 @@ def test_uint8_and_fp16_ingest_equal_the_widened_fp32_batch(golden, scale, hw):
     assert torch.equal(m.infer(xs)[0].clone(), m.infer(xs.contiguous().float() / 255)[0])
 
 
-def test_predict_uint8_host_tensor_matches_fp32_path():
+def test_predict_uint8_host_tensor_matches_fp32_path(chunk_small_batches):
     """A pinned uint8 host batch (a quarter of the fp32 upload) through the chunk-pipelined predictor gives exactly the
     detections of the same images fed as fp32 / 255."""
     from oracle.weights import fill_state_dict_
@@ -418,7 +433,30 @@ def test_predict_uint8_host_tensor_matches_fp32_path():
     assert np.asarray(r8[0].orig_img).dtype == np.uint8 and np.asarray(r8[0].orig_img).shape == (64, 64, 3)
 
 
-def test_predict_alternating_batch_shapes_and_plan_cache_bound():
+def test_predict_single_chunk_async_calls_alternate_lanes():
+    """Small uploads are not chunked: every predict() is one asynchronous chunk and successive calls alternate between
+    the two lanes / plan slots (two batches in flight); results read one call behind stay those of their own batch."""
+    from oracle.weights import fill_state_dict_
+    from yololite import YOLOLite
+
+    yl = YOLOLite("yolo11n.yaml")
+    fill_state_dict_(yl.model)
+    g = torch.Generator().manual_seed(21)
+    xs = [torch.randint(0, 256, (16, 3, 64, 64), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    kw = dict(imgsz=64, conf=0.001, verbose=False, device=0, batch=16)
+    want = [[r.boxes.data.cpu().numpy() for r in yl.predict(x.cuda(), **kw)] for x in xs]
+    assert yl.predictor._chunking(xs[0]) == -1
+    prev = None
+    for it in range(7):
+        res = yl.predict(xs[it % 3], **kw)
+        if prev is not None:
+            for r, w in zip(prev[1], want[prev[0]]):
+                assert np.array_equal(r.boxes.data.cpu().numpy(), w)
+        prev = (it % 3, res)
+    assert yl.predictor.model.__dict__["_yl_pipe"]["next_lane"] in (0, 1)
+
+
+def test_predict_alternating_batch_shapes_and_plan_cache_bound(chunk_small_batches):
     """(a) a full host batch followed by a partial one (and back) must not corrupt the earlier, still
     unread Results: staging states are kept per shape and side streams are drained before anything is freed;
     (b) the per-model plan cache is bounded (LRU) however many shapes / NMS settings stream through."""

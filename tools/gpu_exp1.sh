@@ -1,0 +1,14 @@
+#!/bin/bash
+TAG=${1:-e1}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q --timeout 240 -x > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest.log; tail -15 $OUT/pytest.log
+timeout 120 python tools/timeline.py n 1 --epi > $OUT/timeline_n1_epi.txt 2>&1; tail -3 $OUT/timeline_n1_epi.txt
+timeout 120 python tools/layer_times.py n 64 > $OUT/layers_n64.txt 2>&1; tail -1 $OUT/layers_n64.txt
+timeout 400 python bench.py --no-extras --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; python - <<PY
+import json
+d=json.loads(open("$OUT/bench.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","value_serial","ms_per_step")}, d["bs1_latency_ms"]["p50"], d["e2e"]["value"], d["e2e_u8_input"]["value"])
+print(d["kernel_breakdown"])
+PY
+tail -3 $OUT/bench.err

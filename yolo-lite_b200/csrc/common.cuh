@@ -102,6 +102,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_f(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// NMS candidate key helpers (nms.cu, and the Detect class-filter epilogue of conv_tc.cu): a candidate is
+//   key = (~ordered(score)) << 32 | (anchor * nc + class)
+// so ascending key order == descending score with ties broken by the reference's row order.
+__device__ __forceinline__ uint32_t score_to_desc(float s) {
+    uint32_t b = __float_as_uint(s);
+    uint32_t ordered = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    return ~ordered;
+}
+__device__ __forceinline__ float desc_to_score(uint32_t d) {
+    uint32_t ordered = ~d;
+    uint32_t b = ordered ^ ((ordered >> 31) ? 0x80000000u : 0xffffffffu);
+    return __uint_as_float(b);
+}
+
 // One lane of the (fully active) warp is elected; the compiler knows a single lane runs the guarded code.
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;

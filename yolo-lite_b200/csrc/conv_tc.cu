@@ -82,6 +82,9 @@ struct ConvTcParams {
     int det_nc, det_A, det_anchor0, det_hw, det_w;
     float det_stride;
     long long det_M;             // valid pixels (rows beyond it belong to the ragged last tile)
+    float det_conf;              // YL_DET_CLS_FILTER: confidence threshold (strict >)
+    uint32_t* det_cand_counts;   //   per-image candidate counters of the NMS workspace
+    unsigned long long* det_cand_keys;  // per-image key lists, `det_A` entries each
     unsigned long long* dbg;     // optional timeline slot (8 x %globaltimer ns, written by CTA 0): yl_debug_timeline
 };
 
@@ -114,6 +117,46 @@ __device__ __forceinline__ void tmem_ld_cw<32>(uint32_t taddr, uint32_t (&r)[32]
 // known, writes (cx, cy, w, h) * stride; class mode writes sigmoid(logit).  Consecutive lanes hold consecutive
 // pixels = consecutive anchors, so every channel row of the (B, 4+nc, A) prediction gets 128-byte coalesced
 // stores (head.py:95-126, block.py:51-69, tal.py:326-350).
+// YL_DET_CLS_FILTER: running best class of this thread's pixel over the accumulator chunks; after the last chunk every
+// passing anchor (best > conf, strict; ties keep the lowest class: utils/ops.py:203, 242-244) is appended to its
+// image's candidate list with the same key the NMS filter kernel would build from the stored score.  Lanes are
+// grouped by image (a 128-pixel tile may straddle two images) and each group does ONE atomicAdd.
+template <int CW>
+__device__ __forceinline__ void det_filter_chunk(const ConvTcParams& p, const float (&v)[CW], int c, long long m, int lane,
+                                                 float& best, int& bestc) {
+    if (c == 0) {
+        best = -INFINITY;
+        bestc = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+        const int ch = c * CW + i;
+        if (ch < p.det_nc) {
+            const float sc = __fdividef(1.f, 1.f + __expf(-v[i]));   // the value YL_DET_CLS would have stored
+            if (sc > best) {
+                best = sc;
+                bestc = ch;
+            }
+        }
+    }
+    if (c != p.nchunks - 1) return;
+    const bool emit = (m < p.det_M) && (best > p.det_conf);
+    if (__ballot_sync(0xffffffffu, emit) == 0u) return;
+    const int b = emit ? (int)(m / p.det_hw) : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, b);
+    if (emit) {
+        const int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(p.det_cand_counts + b, (uint32_t)__popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        const uint32_t pos = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+        const int al = (int)(m - (long long)b * p.det_hw);
+        const uint32_t idx = (uint32_t)(p.det_anchor0 + al) * (uint32_t)p.det_nc + (uint32_t)bestc;
+        p.det_cand_keys[(unsigned long long)b * (unsigned long long)p.det_A + pos] =
+            ((unsigned long long)score_to_desc(best) << 32) | idx;
+    }
+}
+
 template <int CW>
 __device__ __forceinline__ void det_decode_chunk(const ConvTcParams& p, const float (&v)[CW], int c, long long m,
                                                  float (&dist)[4]) {
@@ -185,6 +228,8 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
     int pend = 0, pc0 = 0, pw0 = 0, ph0 = 0, pi0 = 0;  // filled tile whose TMA store is not issued yet
     uint32_t pbuf = 0;
     float det_dist[4] = {0.f, 0.f, 0.f, 0.f};  // decode mode: DFL distances (l, t, r, b) of this thread's pixel
+    float det_best = -INFINITY;                // class-filter mode: best score / class of this thread's pixel
+    int det_bestc = 0;
 
     int lt = g;
     for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, lt += 2) {
@@ -255,7 +300,10 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                         v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
                     }
                 }
-                if (p.det_mode) det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
+                if (p.det_mode == YL_DET_CLS_FILTER)
+                    det_filter_chunk<CW>(p, v, c, w0 + row, lane, det_best, det_bestc);
+                else if (p.det_mode)
+                    det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
                 if (!p.store_y) continue;
                 if (leader && g == 0 && lt == 0 && c < 2) YL_STAMP(c == 0 ? 9 : 13);
                 if (u == 0) {
@@ -682,6 +730,10 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
             if (d.reg_max != 16 || y.c != 64) NOPE("Detect box decode is built for reg_max == 16 (64 channels)");
         } else if (d.mode == YL_DET_CLS) {
             if (y.c != d.nc || y.c > 256) NOPE("Detect class decode needs co == nc <= 256");
+        } else if (d.mode == YL_DET_CLS_FILTER) {
+            if (y.c != d.nc || y.c > 256) NOPE("Detect class filter needs co == nc <= 256");
+            if (!d.cand_ws || !(d.conf >= 0.f && d.conf <= 1.f)) NOPE("Detect class filter needs a workspace and conf in [0,1]");
+            if ((long long)d.A * d.nc >= (1ll << 32)) NOPE("A * nc must fit 32 bits");
         } else {
             NOPE("bad Detect-decode mode");
         }
@@ -765,7 +817,10 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     // second wave runs almost alone; halving the tile (2 CTAs/SM, 256 columns each) keeps every tile resident at once.
     {
         const long long m_est = ceil_div64((long long)x.n * Ho * Wo, 128);
-        if (n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && env_int("YL_NSPLIT", 1)) n_tiles = 2;
+        // (the class-filter epilogue needs every class of a pixel in ONE tile)
+        if (n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && env_int("YL_NSPLIT", 1) &&
+            a->det.mode != YL_DET_CLS_FILTER)
+            n_tiles = 2;
     }
     p.co_tile = ceil_div(ceil_div(co16, n_tiles), 16) * 16;
 
@@ -961,6 +1016,12 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
         p.det_w = x.w;
         p.det_stride = a->det.stride;
         p.det_M = (long long)x.n * x.h * x.w;
+        if (a->det.mode == YL_DET_CLS_FILTER) {
+            p.det_conf = a->det.conf;
+            p.det_cand_counts = reinterpret_cast<uint32_t*>(a->det.cand_ws);
+            p.det_cand_keys = reinterpret_cast<unsigned long long*>(
+                reinterpret_cast<char*>(a->det.cand_ws) + ((size_t)x.n * 4 + 255) / 256 * 256);
+        }
     }
     p.wearly = env_int("YL_WEARLY", 1);
     p.bias = a->bias;

@@ -29,16 +29,6 @@ constexpr int kSortCap = 16384;  // keys sorted in shared memory per round
 constexpr int kChunk = 512;      // candidates resolved per bitmask round
 constexpr int kMaskWords = kChunk / 32;
 
-__device__ __forceinline__ uint32_t score_to_desc(float s) {
-    uint32_t b = __float_as_uint(s);
-    uint32_t ordered = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
-    return ~ordered;
-}
-__device__ __forceinline__ float desc_to_score(uint32_t d) {
-    uint32_t ordered = ~d;
-    uint32_t b = ordered ^ ((ordered >> 31) ? 0x80000000u : 0xffffffffu);
-    return __uint_as_float(b);
-}
 
 // ---------------------------------------------------------------------------------------------- filter
 template <int VEC, bool MULTI>
@@ -661,6 +651,34 @@ __global__ void scale_boxes_kernel(float* __restrict__ dets, const int32_t* __re
     }
 }
 
+static int launch_select(const float* pred, int B, int nc, int A, size_t cap, const uint32_t* cand_counts,
+                         const unsigned long long* keys, double iou_thres, int agnostic, int max_det, int max_nms,
+                         float max_wh, float* out, int32_t* counts, cudaStream_t s) {
+    SelParams p;
+    p.pred = pred;
+    p.nc = nc;
+    p.A = A;
+    p.cap = cap;
+    p.counts = cand_counts;
+    p.keys = keys;
+    p.thr = thr_to_float(iou_thres);
+    thr_midpoint(p.thr, &p.thr_mid, &p.thr_tie_up);
+    p.max_wh = agnostic ? 0.f : max_wh;
+    p.max_det = max_det;
+    p.max_nms = max_nms;
+    p.kept_in_smem = 1;
+    p.kept_ws = nullptr;
+    p.kept_keys_ws = nullptr;
+    p.out = out;
+    p.out_counts = counts;
+    p.keep = nullptr;
+    const size_t smem = sel_smem_bytes(max_det, true);
+    YL_CHECK((int)smem <= g_sel_max_smem, YL_ERR_UNSUPPORTED, "NMS needs %zu B shared memory (yl_init called?)", smem);
+    nms_select_kernel<0><<<B, kSelThreads, smem, s>>>(p);
+    YL_LAUNCH_OK("nms_select_kernel");
+    return YL_OK;
+}
+
 }  // namespace yl
 
 extern "C" {
@@ -709,30 +727,29 @@ int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, do
     }
     YL_LAUNCH_OK("nms_filter_kernel");
 
-    yl::SelParams p;
-    p.pred = pred;
-    p.nc = nc;
-    p.A = A;
-    p.cap = cap;
-    p.counts = cand_counts;
-    p.keys = keys;
-    p.thr = yl::thr_to_float(iou_thres);
-    yl::thr_midpoint(p.thr, &p.thr_mid, &p.thr_tie_up);
-    p.max_wh = agnostic ? 0.f : max_wh;
-    p.max_det = max_det;
-    p.max_nms = max_nms;
-    p.kept_in_smem = 1;
-    p.kept_ws = nullptr;
-    p.kept_keys_ws = nullptr;
-    p.out = out;
-    p.out_counts = counts;
-    p.keep = nullptr;
-    const size_t smem = yl::sel_smem_bytes(max_det, true);
-    YL_CHECK((int)smem <= yl::g_sel_max_smem, YL_ERR_UNSUPPORTED, "NMS needs %zu B shared memory (yl_init called?)",
-             smem);
-    yl::nms_select_kernel<0><<<B, yl::kSelThreads, smem, s>>>(p);
-    YL_LAUNCH_OK("nms_select_kernel");
+    return yl::launch_select(pred, B, nc, A, cap, cand_counts, keys, iou_thres, agnostic, max_det, max_nms, max_wh, out,
+                             counts, s);
+}
+
+int yl_nms_begin(void* workspace, size_t workspace_bytes, int B, void* stream) {
+    YL_CHECK(workspace && B > 0 && workspace_bytes >= (size_t)B * 4, YL_ERR_ARG, "bad nms_begin arguments");
+    YL_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * 4, (cudaStream_t)stream));
     return YL_OK;
+}
+
+int yl_nms_select(const float* pred, int B, int nc, int A, double iou_thres, int agnostic, int max_det, int max_nms,
+                  float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* counts, void* stream) {
+    YL_CHECK(pred && out && counts && workspace, YL_ERR_ARG, "null pointer");
+    YL_CHECK(B > 0 && nc > 0 && nc <= 1024 && A > 0, YL_ERR_ARG, "bad dims B=%d nc=%d A=%d", B, nc, A);
+    YL_CHECK((long long)A * nc < (1ll << 32), YL_ERR_ARG, "A*nc must fit 32 bits");
+    YL_CHECK(max_det > 0 && max_det <= 1024, YL_ERR_ARG, "max_det must be in [1,1024]");
+    YL_CHECK(max_nms > 0 && iou_thres >= 0. && iou_thres <= 1., YL_ERR_ARG, "bad thresholds");
+    YL_CHECK(workspace_bytes >= yl_nms_workspace_bytes(B, A, nc, 0), YL_ERR_WORKSPACE, "NMS workspace too small");
+    uint32_t* cand_counts = reinterpret_cast<uint32_t*>(workspace);
+    unsigned long long* keys =
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + yl::align_up((size_t)B * 4, 256));
+    return yl::launch_select(pred, B, nc, A, (size_t)A, cand_counts, keys, iou_thres, agnostic, max_det, max_nms, max_wh,
+                             out, counts, (cudaStream_t)stream);
 }
 
 size_t yl_nms_boxes_workspace_bytes(int n) {

@@ -53,10 +53,13 @@ class DetEpilogue(C.Structure):
         ("A", C.c_int32),
         ("anchor0", C.c_int32),
         ("stride", C.c_float),
+        ("conf", C.c_float),
+        ("_pad", C.c_int32),
+        ("cand_ws", C.c_void_p),
     ]
 
 
-DET_NONE, DET_BOX, DET_CLS = 0, 1, 2
+DET_NONE, DET_BOX, DET_CLS, DET_CLS_FILTER = 0, 1, 2, 3
 
 
 class LbImage(C.Structure):
@@ -130,6 +133,9 @@ _PROTOTYPES = {
     "yl_nms_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "yl_nms_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "yl_nms_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yl_nms_boxes_workspace_bytes": (C.c_size_t, [C.c_int]),
     "yl_nms_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p,
                                C.c_void_p, C.c_void_p]),

@@ -110,11 +110,13 @@ class DetEpilogue:
     """Fused Detect decode of a head conv (see yl_det_epilogue): `pred` is the (B, 4+nc, A) fp32 prediction."""
 
     pred: torch.Tensor
-    mode: int            # _C.DET_BOX | _C.DET_CLS
+    mode: int            # _C.DET_BOX | _C.DET_CLS | _C.DET_CLS_FILTER
     reg_max: int
     nc: int
     anchor0: int
     stride: float
+    conf: float = 0.0                      # DET_CLS_FILTER: confidence threshold of the NMS that follows
+    cand_ws: torch.Tensor | None = None    # DET_CLS_FILTER: NMS workspace the candidates are appended to
 
 
 class NoOutput:
@@ -137,6 +139,8 @@ def conv_args(x: View, y, pc: PackedConv, stride=1, act=True, res: View | None =
         a.det.pred = det.pred.data_ptr()
         a.det.mode, a.det.reg_max, a.det.nc = det.mode, det.reg_max, det.nc
         a.det.A, a.det.anchor0, a.det.stride = det.pred.shape[2], det.anchor0, float(det.stride)
+        if det.mode == _C.DET_CLS_FILTER:
+            a.det.conf, a.det.cand_ws = float(det.conf), det.cand_ws.data_ptr()
     a.res = res.ct() if res is not None else _C.null_tensor()
     a.y_up = y_up.ct() if y_up is not None else _C.null_tensor()
     a.w, a.bias = pc.w.data_ptr(), pc.bias.data_ptr()

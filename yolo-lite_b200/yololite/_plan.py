@@ -69,6 +69,10 @@ class Builder:
         self.meta: list[dict] = []
         self.ingest: NchwInput | None = None
         self.want_raw = True               # Detect: also write the raw head maps (module-level API)
+        # single-label NMS arguments (conf, ...) of the step this plan ends with, when the Detect head may run the class
+        # filter in its conv epilogues (set by BaseModel._get_plan); the head then fills `cand_ws`
+        self.nms_fuse_conf: float | None = None
+        self.cand_ws: torch.Tensor | None = None
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -193,20 +197,25 @@ class Builder:
             raise RuntimeError(f"fused Detect decode rejected by the tcgen05 path: {x.c}->{pc.co} k{k}")
         out_bytes = opx * pc.co * esz * u * u if store else 0
         if det is not None:   # decoded rows of the prediction: 4 box values or nc scores per anchor, fp32
-            out_bytes += opx * (4 if det.mode == _C.DET_BOX else det.nc) * 4
+            out_bytes += opx * (4 if det.mode == _C.DET_BOX else (0 if det.mode == _C.DET_CLS_FILTER else det.nc)) * 4
         self._push(self.lib.yl_conv_bn_act, C.byref(a), keep=(a, pc, det), kind="conv_tc" if tc else "conv_direct",
                    bytes_=x.n * x.h * x.w * x.c * 2 + out_bytes + k * k * x.c * pc.co * 2
                    + (opx * pc.co * 2 if res is not None else 0) + (4 * opx * pc.co * esz if y_up is not None else 0),
                    flops=2 * opx * pc.co * x.c * k * k,
                    desc=f"{x.c}->{pc.co} k{k}s{stride} {x.h}x{x.w}" + (" +res" if res is not None else "")
                    + (" up2" if upsample else "") + (" +up2" if y_up is not None else "")
-                   + (" f32" if esz == 4 and store else "") + (" +decode" if det is not None else ""),
+                   + (" f32" if esz == 4 and store else "")
+                   + ("" if det is None else (" +filter" if det.mode == _C.DET_CLS_FILTER else " +decode")),
                    reads=(x, res),
                    # the fused decode writes its own block of the prediction: rows (box | class) x this level's anchors;
                    # blocks of different launches are disjoint, a reader of the whole tensor (NMS) depends on all of them
                    writes=(y if store else None, y_up,
-                           None if det is None else (det.pred, 2 * det.anchor0 + (det.mode == _C.DET_CLS),
-                                                     2 * det.anchor0 + (det.mode == _C.DET_CLS) + 1)))
+                           None if det is None or det.mode == _C.DET_CLS_FILTER else
+                           (det.pred, 2 * det.anchor0 + (det.mode == _C.DET_CLS), 2 * det.anchor0 + (det.mode == _C.DET_CLS) + 1),
+                           # the class filter appends to the candidate lists: ordered after yl_nms_begin (which wrote the
+                           # whole workspace), unordered among the levels (atomic appends), all before yl_nms_select
+                           None if det is None or det.mode != _C.DET_CLS_FILTER else
+                           (det.cand_ws, 1 + det.anchor0, 2 + det.anchor0)))
         return y if store else None
 
     def stem_fused(self, x: NchwInput, pc0: PackedConv, pc1: PackedConv, act0: bool, act1: bool, out=None) -> View:
@@ -281,12 +290,35 @@ class Builder:
                    writes=(y,))
         return y
 
+    def nms_begin(self, B: int, A: int, nc: int) -> torch.Tensor:
+        """Workspace of a step whose class filter runs inside the Detect head convs (DET_CLS_FILTER): allocates it and
+        records the launch that zeroes its candidate counters (the head convs that append candidates depend on it)."""
+        ws = torch.empty(max(int(self.lib.yl_nms_workspace_bytes(B, A, nc, 0)), 16), dtype=torch.uint8, device=self.device)
+        self.buffers.append(ws)
+        self.cand_ws = ws
+        self._push(self.lib.yl_nms_begin, ws.data_ptr(), ws.numel(), B, keep=(ws,), kind="nms_begin", bytes_=B * 4,
+                   writes=(ws,))
+        return ws
+
     def nms(self, pred: torch.Tensor, conf, iou, classes=None, agnostic=False, multi_label=False, max_det=300,
             max_nms=30000, max_wh=7680.0):
         """Batched NMS as the last launches of the plan (so a whole step is the ingest + ONE graph launch): the
         workspace, (B, max_det, 6) detections and (B,) counts are plan-owned static buffers."""
         B, C4, A = pred.shape
         nc = C4 - 4
+        if self.cand_ws is not None:
+            # the Detect head already filtered: candidates are in the workspace, only the per-image select remains
+            assert not multi_label and classes is None and self.nms_fuse_conf == float(conf)
+            ws = self.cand_ws
+            out = torch.empty((B, max_det, 6), dtype=torch.float32, device=self.device)
+            counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+            self.buffers += [out, counts]
+            self._push(self.lib.yl_nms_select, pred.data_ptr(), B, nc, A, float(iou), int(agnostic), int(max_det),
+                       int(max_nms), float(max_wh), ws.data_ptr(), ws.numel(), out.data_ptr(), counts.data_ptr(),
+                       keep=(ws, out, counts, pred), kind="nms_select", bytes_=B * 4 * A * 4,
+                       desc=f"iou {iou} max_det {max_det} (filter fused into the head)", reads=(pred, ws),
+                       writes=(out, counts))
+            return out, counts
         ws = torch.empty(max(int(self.lib.yl_nms_workspace_bytes(B, A, nc, int(multi_label))), 16), dtype=torch.uint8,
                          device=self.device)
         out = torch.empty((B, max_det, 6), dtype=torch.float32, device=self.device)
@@ -392,15 +424,18 @@ class Plan:
         n = len(self.calls)
         s = _C.stream_ptr()
         times = []
+        # the one exception to idempotence: head convs with the fused class filter APPEND candidates (atomic counters
+        # zeroed by yl_nms_begin); they are issued once per pass so the select kernel sees each candidate once
+        once = [" +filter" in md["desc"] for md in self.meta]
         for _ in range(reps):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
-            ev[0].record()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n)]
             for i, (fn, args, _) in enumerate(self.calls):
-                for _k in range(inner):
+                ev[2 * i].record()
+                for _k in range(1 if once[i] else inner):
                     _C.check(fn(*args, s), fn.__name__)
-                ev[i + 1].record()
+                ev[2 * i + 1].record()
             torch.cuda.synchronize(self.device)
-            times.append([ev[i].elapsed_time(ev[i + 1]) / inner for i in range(n)])
+            times.append([ev[2 * i].elapsed_time(ev[2 * i + 1]) / (1 if once[i] else inner) for i in range(n)])
         t = torch.tensor(times).median(0).values.tolist()
         return t
 

@@ -91,8 +91,12 @@ class DetectionPredictor:
 
     #: host batches are ingested in this many chunks (H2D of chunk k+1 overlaps compute of chunk k)
     pipeline_chunks = 4
-    #: never split below this many images per chunk (tiny plans waste the 148 SMs)
+    #: never split below this many images per chunk (tiny plans waste the 148 SMs) ...
     pipeline_min_chunk = 8
+    #: ... nor below this many upload bytes per chunk: chunking exists to start computing before the whole batch has
+    #: crossed PCIe; when a chunk's upload (~18 us per MB) is short next to its kernels (fp16 / uint8 batches), the
+    #: smaller plans only cost GPU efficiency, and successive predict() calls already overlap upload and compute
+    pipeline_min_chunk_bytes = 48 << 20
     #: chunks in flight on the GPU (1 or 2): consecutive chunks alternate between two streams / plan slots, so
     #: the launch-latency-bound small layers of one chunk overlap the bandwidth-bound layers of the other
     in_flight = 2
@@ -100,15 +104,17 @@ class DetectionPredictor:
     pipeline_states = 3
 
     def _chunking(self, im):
-        """Number of ingest chunks for a host tensor batch (1 = plain path)."""
+        """Number of ingest chunks for a host tensor batch: n > 1 = chunk-pipelined, -1 = asynchronous pipeline with the
+        whole batch as one chunk, 1 = plain synchronous-order path (device tensors, lists of images)."""
         if not isinstance(im, torch.Tensor) or im.is_cuda or im.dim() != 4 \
                 or im.dtype not in (torch.float32, torch.float16, torch.uint8) or not im.is_contiguous():
             return 1
         b = im.shape[0]
+        nbytes = im.numel() * im.element_size()
         for n in range(int(self.pipeline_chunks), 1, -1):
-            if b % n == 0 and b // n >= self.pipeline_min_chunk:
+            if b % n == 0 and b // n >= self.pipeline_min_chunk and nbytes // n >= self.pipeline_min_chunk_bytes:
                 return n
-        return 1
+        return -1          # asynchronous pipeline, whole batch as one chunk
 
     def _pipelined(self, im_host, n_chunks):
         """preprocess + inference + NMS of a host fp32 batch, chunk-pipelined.  Returns (device batch, dets,
@@ -170,19 +176,21 @@ class DetectionPredictor:
                 buf[k * cb:(k + 1) * cb].copy_(im_host[k * cb:(k + 1) * cb], non_blocking=True)
                 st["events"][k].record(st["copy"])
         model = self.model.model
-        fly = max(1, min(int(self.in_flight), n_chunks, 2))
+        fly = max(1, min(int(self.in_flight), 2))
         lanes = st["lanes"][:fly]
-        for ln in lanes:
-            if pipe["snap"] is not None:
-                ln.wait_event(pipe["snap"])      # the previous call's snapshot of dets / counts has been taken
+        lane0 = pipe.get("next_lane", 0)         # chunks (and single-chunk calls) keep alternating lanes across calls
+        pipe["next_lane"] = (lane0 + n_chunks) % fly
         for k in range(n_chunks):
-            ln = lanes[k % fly]
+            li = (lane0 + k) % fly
+            ln = lanes[li]
             with torch.cuda.stream(ln):
                 ln.wait_event(st["events"][k])
                 # model + NMS of the chunk are one CUDA-graph launch; its plan-owned outputs are gathered into the
                 # batch-level buffers (115 KB per 16 images)
                 d, c = model.infer_nms(buf[k * cb:(k + 1) * cb], a.conf, a.iou, a.classes, a.agnostic_nms, False,
-                                       a.max_det, slot=k % fly)
+                                       a.max_det, slot=li)
+                if pipe["snap"] is not None:
+                    ln.wait_event(pipe["snap"])  # the previous call's snapshot of the batch-level dets / counts is taken
                 st["dets"][k * cb:(k + 1) * cb].copy_(d, non_blocking=True)
                 st["counts"][k * cb:(k + 1) * cb].copy_(c, non_blocking=True)
         post = st["post"]
@@ -265,7 +273,8 @@ class DetectionPredictor:
             for self.batch in self.dataset:
                 paths, im0s, s = self.batch
                 n_chunks = self._chunking(im0s)
-                if n_chunks > 1:
+                if n_chunks != 1:
+                    n_chunks = abs(n_chunks)
                     # host tensor batch: copy / model / NMS run chunk-pipelined (preprocess+inference timed together)
                     with profilers[1]:
                         im, dets, counts, post = self._pipelined(im0s, n_chunks)

@@ -36,6 +36,9 @@ class Detect(YLModule):
     fuse_decode = True
     #: put the per-level box / class chains on parallel graph branches
     parallel_branches = True
+    #: engine path (plan ends with single-label NMS): run the confidence filter + best-class selection of
+    #: non_max_suppression inside the class convs' epilogue instead of writing and re-reading (B, nc, A) scores
+    fuse_filter = True
 
     def __init__(self, nc=80, ch=()):
         super().__init__()
@@ -73,7 +76,9 @@ class Detect(YLModule):
             raise RuntimeError("Detect.stride is unset (it is filled in by DetectionModel)")
         nbox = 4 * self.reg_max
         want_raw = getattr(g, "want_raw", True)
-        fuse = self.fuse_decode and self.reg_max == 16 and self.nc <= 256 and self.nc % 8 == 0
+        c2, c3 = self.cv2[0][-1].in_channels, self.cv3[0][-1].in_channels
+        fuse = (self.fuse_decode and self.reg_max == 16 and self.nc <= 256 and self.nc % 8 == 0
+                and c2 % 8 == 0 and c3 % 8 == 0)          # what the tcgen05 path needs; otherwise the decode kernel
         raws = []
         if not fuse:
             for i, x in enumerate(feats):
@@ -93,6 +98,12 @@ class Detect(YLModule):
         A = sum(x.h * x.w for x in feats)
         y = torch.empty((n, 4 + self.nc, A), dtype=torch.float32, device=g.device)
         g.buffers.append(y)
+        import os
+
+        conf = getattr(g, "nms_fuse_conf", None)
+        filt = (self.fuse_filter and conf is not None and not want_raw and self.nc <= 256
+                and A * self.nc < (1 << 32) and os.environ.get("YL_FUSE_FILTER", "1") != "0")
+        cand_ws = g.nms_begin(n, A, self.nc) if filt else None
         a0 = 0
         for i, x in enumerate(feats):
             raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32) if want_raw else None
@@ -104,7 +115,11 @@ class Detect(YLModule):
                 with g.lane(lane):
                     t = emit_any(g, branch[:-1], x)
                     last = branch[-1]
-                    det = _ops.DetEpilogue(y, mode, self.reg_max, self.nc, a0, float(self.stride[i]))
+                    if filt and mode == _C.DET_CLS:
+                        det = _ops.DetEpilogue(y, _C.DET_CLS_FILTER, self.reg_max, self.nc, a0, float(self.stride[i]),
+                                               conf=conf, cand_ws=cand_ws)
+                    else:
+                        det = _ops.DetEpilogue(y, mode, self.reg_max, self.nc, a0, float(self.stride[i]))
                     g.conv(t, packed(last, None, last), 1, act=False, out=raw.slice(lo, cnt) if want_raw else None,
                            out_dtype=torch.float32, det=det, store=want_raw)
             if want_raw:

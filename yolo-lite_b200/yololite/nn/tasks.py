@@ -347,6 +347,8 @@ class BaseModel(YLModule):
             with torch.cuda.device(dev):
                 g = _plan.Builder(dev)
                 g.want_raw = bool(want_raw)   # Detect writes its raw (B, H, W, no) maps only on request
+                if nms is not None and not nms[4] and nms[2] is None:
+                    g.nms_fuse_conf = float(nms[0])   # single-label, no class filter: the head may filter in its epilogue
                 static_in = torch.zeros(tuple(shape), dtype=torch.float32, device=dev)
                 xin = g.input_nchw(static_in)
                 y, raws = self._emit(g, xin)
