@@ -59,11 +59,13 @@ int yl_init(int device);
 /* Programmatic dependent launch: by default every kernel of the library is launched with the programmatic
  * stream-serialization attribute (its prologue may overlap the previous kernel of the stream; it executes
  * griddepcontrol.wait before touching activations).  yl_set_pdl(0) makes subsequent launches plain (used for a
- * launch that follows a cross-stream event wait); returns the previous setting.  Process-wide, not thread-safe. */
+ * launch that follows a cross-stream event wait); returns the previous setting.  The setting belongs to the CALLING
+ * THREAD (thread-local, like the CUDA current device): other threads' launches are unaffected. */
 int yl_set_pdl(int enabled);
 /* Debug aid: the next `capacity` tcgen05 conv launches record 8 %globaltimer stamps (ns) of CTA 0 into
  * device_buf[launch][8]: start, prologue done, dependency wait done, first operands landed, first accumulator
- * ready, last store issued, staging drained, exit.  NULL disables.  Not for production use. */
+ * ready, last store issued, staging drained, exit.  NULL disables.  Arms the calling thread's launches only
+ * (thread-local); a separate instantiation of the kernel carries the stamps, production launches never pay for them. */
 int yl_debug_timeline(unsigned long long* device_buf, int capacity);
 
 /* ---- weight preparation (one-time) ----------------------------------------------------------------------

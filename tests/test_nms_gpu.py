@@ -159,6 +159,48 @@ def test_nms_stress_dense_full_size_vs_oracle(ops, multi_label):
         np.testing.assert_array_equal(d[i, : c[i]], ref[j], err_msg=f"image {i}")
 
 
+def test_nms_classwise_path_and_its_fallbacks_vs_oracle(ops):
+    """The per-class select path (class offsets separate the classes) and every condition that sends an image back to
+    the general path, one image each in ONE batch, bit-exact against the oracle:
+      0  ordinary image (class-wise)            1  boxes whose x extent exceeds max_wh: classes DO overlap after the offset
+      2  one class with > 256 candidates        3  empty image           4  a NaN box           5  small max_wh (extent test fails)
+    plus the same batch with agnostic NMS, a class list and tiny max_det / max_nms."""
+    from oracle import nms_ref
+
+    g = np.random.default_rng(31)
+    B, A, nc = 5, 1500, 80
+    p = np.zeros((B, 4 + nc, A), np.float32)
+    p[:, 0:2] = g.uniform(0, 640, (B, 2, A))
+    p[:, 2:4] = g.uniform(8, 200, (B, 2, A))
+    k = A // 2                                                      # near-duplicates so that suppression happens
+    src = g.integers(0, A, k)
+    p[:, 0:4, :k] = p[:, 0:4, src] + g.normal(0, 2.0, (B, 4, k)).astype(np.float32)
+    logits = g.normal(-3.0, 2.0, (B, nc, A))
+    p[:, 4:] = 1.0 / (1.0 + np.exp(-logits))
+    # image 1: centres spread over 0..16000 px with huge boxes -> different classes overlap after `+ cls * 7680`
+    p[1, 0] = g.uniform(0, 16000, A)
+    p[1, 2] = g.uniform(2000, 9000, A)
+    p[1, 3] = g.uniform(300, 640, A)
+    p[1, 1] = g.uniform(200, 400, A)
+    # image 2: everything is class 7 (one segment of ~1500 candidates)
+    p[2, 4:] = 0.0
+    p[2, 4 + 7] = g.uniform(0.3, 0.9, A)
+    # image 3: nothing passes
+    p[3, 4:] = 0.01
+    # image 4: a NaN coordinate among ordinary boxes
+    p[4, 0, 17] = np.nan
+    for kw in (dict(conf_thres=0.25, iou_thres=0.6), dict(conf_thres=0.25, iou_thres=0.6, agnostic=True),
+               dict(conf_thres=0.3, iou_thres=0.5, classes=[0, 7, 33]), dict(conf_thres=0.25, iou_thres=0.6, max_det=7),
+               dict(conf_thres=0.25, iou_thres=0.6, max_nms=100), dict(conf_thres=0.25, iou_thres=0.6, max_wh=300),
+               dict(conf_thres=0.05, iou_thres=0.7, multi_label=True)):
+        res = run_gpu(ops, p, **kw)
+        ref = nms_ref.non_max_suppression(p, **kw)
+        assert [len(r) for r in res] == [len(r) for r in ref], kw
+        for i, (a, r) in enumerate(zip(res, ref)):
+            np.testing.assert_array_equal(a, r, err_msg=f"{kw} image {i}")
+    assert len(ref[0]) > 20
+
+
 def test_nms_argument_errors(ops):
     from yololite import _C
 

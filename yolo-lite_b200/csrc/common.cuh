@@ -36,6 +36,27 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Division by a launch-time constant without the ~25-instruction integer-division sequence: q = umulhi(x, mul) >> shr
+// for 0 <= x < 2^31 (d == 1 is special-cased).  Host side builds it, device side applies it.
+struct FastDiv {
+    uint32_t mul, shr, d;
+};
+static inline FastDiv make_fastdiv(int d_) {
+    FastDiv f;
+    f.d = (uint32_t)(d_ < 1 ? 1 : d_);
+    if (f.d == 1) {
+        f.mul = 0;
+        f.shr = 0;
+        return f;
+    }
+    uint32_t lg = 0;
+    while ((1ull << lg) < f.d) ++lg;
+    const uint32_t pw = 31 + lg;
+    f.mul = (uint32_t)(((1ull << pw) + f.d - 1) / f.d);
+    f.shr = pw - 32;
+    return f;
+}
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Driver entry point for cuTensorMapEncodeTiled, resolved through the runtime so the
@@ -75,6 +96,16 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 // Allow the dependent kernel of the stream to be scheduled once every CTA of this grid has got here or exited.
 __device__ __forceinline__ void griddep_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ int fast_div(int x, const FastDiv& f) {
+    return f.d == 1 ? x : (int)(__umulhi((uint32_t)x, f.mul) >> f.shr);
+}
+// (quotient, remainder) of x / f.d
+__device__ __forceinline__ int fast_divmod(int x, const FastDiv& f, int* rem) {
+    const int q = fast_div(x, f);
+    *rem = x - q * (int)f.d;
+    return q;
 }
 
 // ---------------------------------------------------------------- small device utils

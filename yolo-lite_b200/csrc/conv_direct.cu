@@ -542,8 +542,11 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
     YL_CHECK(x->n <= 65535, YL_ERR_ARG, "batch too large for one launch");
     cudaStream_t s = (cudaStream_t)stream;
     {
-        const char* em = getenv("YL_DW_MMA");
-        if (!(em && *em && atoi(em) == 0)) {
+        static const int use_mma = [] {            // A/B switch, read once per process (never on a later launch)
+            const char* em = getenv("YL_DW_MMA");
+            return !(em && *em && atoi(em) == 0);
+        }();
+        if (use_mma) {
             // tensor-core path: (8 x 16)-pixel tiles, up to 8 channel groups per block, two groups per warp
             const int groups = x->c / 8;
             const int cblocks = yl::ceil_div(groups, 8);
@@ -567,8 +570,10 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
             return YL_OK;
         }
     }
-    const char* e = getenv("YL_DW_STRIP");  // launch-time only (plans are captured into CUDA graphs)
-    const int strip = (e && *e) ? atoi(e) : 2;  // measured: 2-pixel strips are fastest (tools/bench_kernels.py)
+    static const int strip = [] {                  // A/B switch, read once per process
+        const char* e = getenv("YL_DW_STRIP");
+        return (e && *e) ? atoi(e) : 2;            // measured: 2-pixel strips are fastest (tools/bench_kernels.py)
+    }();
     const int P = strip >= 4 ? 4 : (strip >= 2 ? 2 : 1);
     const long long per_image = (long long)x->h * yl::ceil_div(x->w, P) * (x->c / 8);
     YL_CHECK(per_image < (1ll << 31), YL_ERR_ARG, "image too large");

@@ -40,6 +40,7 @@ struct ConvTcParams {
     int tiles_w, tiles_h, tiles_n;
     int TW, TH, TN;              // A-tile box: TW*TH*TN <= 128 rows (pixels), may span images
     int m_tiles, n_tiles, total_tiles;
+    FastDiv fd_ntiles, fd_tiles_w, fd_tiles_h;   // tile index -> (n tile, w tile, h tile, image tile)
     int ksize, stride, pad;
     int ci_pad;                  // K elements per tap in the packed weights
     int kblk, cin_blocks;        // channels per k-iteration, iterations per tap
@@ -72,6 +73,7 @@ struct ConvTcParams {
     const float* bias;
     int n_bias;                  // valid bias entries (co_pad)
     int act;
+    int epi_kind;                // which epilogue instantiation runs (see conv_tc_kernel)
     const __nv_bfloat16* res;
     long long res_cstride;
     int res_coff, res_c;
@@ -93,9 +95,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define YL_STAMP(slot)                                                   \
-    do {                                                                 \
-        if (p.dbg && blockIdx.x == 0) p.dbg[slot] = globaltimer_ns();    \
+// (compiled out of the production instantiation: DBG is a template parameter of the kernel)
+#define YL_STAMP(slot)                                                          \
+    do {                                                                        \
+        if constexpr (DBG) {                                                    \
+            if (p.dbg && blockIdx.x == 0) p.dbg[slot] = globaltimer_ns();       \
+        }                                                                       \
     } while (0)
 
 constexpr int kConvTcThreads = 320;
@@ -209,18 +214,31 @@ __device__ __forceinline__ void det_decode_chunk(const ConvTcParams& p, const fl
 // one TMA store.  With two staging tiles the store of chunk k is issued after the barrier of chunk k+1, so the
 // group never waits for a TMA store to drain its source: one named barrier per store chunk, and the smem read
 // of store k overlaps the TMEM load + math of chunk k+1.
-template <int CW>
+//
+// GENERIC == false is the hot instantiation (bf16 destination, no Detect epilogue; activation / residual are compile-time
+// ACT / RES): ncu showed ~300 warp instructions per 32-column chunk of which only ~160 were the math, the rest runtime
+// flag tests, parameter reloads, swizzle arithmetic and the (disabled) timeline stamps.  GENERIC == true keeps every
+// runtime option (fp32 destination, Detect decode / class filter, no NHWC store).
+template <int CW, bool ACT, bool RES, bool GENERIC, bool DBG>
 __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, int q, int lane, int gtid,
                                                  uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                  uint8_t* stg, const float* sbias) {
+    const bool k_act = GENERIC ? (p.act != 0) : ACT;
+    const bool k_res = GENERIC ? (p.res != nullptr) : RES;
+    const bool k_f32 = GENERIC ? (p.y_f32 != 0) : false;
+    const int k_det = GENERIC ? p.det_mode : 0;
+    const bool k_store = GENERIC ? (p.store_y != 0) : true;
     const int row = q * 32 + lane;
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
     const uint32_t swz_mask = (uint32_t)(p.stg_row_bytes / 16 - 1);  // 1, 3 or 7 sixteen-byte chunks
     const uint32_t row_off = (uint32_t)row * (uint32_t)p.stg_row_bytes;
+    // a row's bytes never cross a 128-byte line (row pitch 32 / 64 / 128), so the swizzle XOR is a per-thread constant
+    const uint32_t swz_xor = ((row_off >> 7) & swz_mask) << 4;
     const uint32_t stg_base = smem_u32(stg);
-    const uint32_t sub_bytes = (uint32_t)CW * (p.y_f32 ? 4u : 2u);
+    const uint32_t sub_bytes = (uint32_t)CW * (k_f32 ? 4u : 2u);
+    const int nchunks = p.nchunks, stg_sub = p.stg_sub, nstore = p.nstore;
     const bool dbl = p.stg_bufs == 2;
     // the first warp of the group owns the TMA stores; one elected lane issues / commits / waits on them
     const bool leader = (gtid < 32) && elect_one();
@@ -233,16 +251,15 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
 
     int lt = g;
     for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, lt += 2) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int w0 = (mt % p.tiles_w) * p.TW;
-        mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * p.TH;
-        const int i0 = (mt / p.tiles_h) * p.TN;
+        int nt, wt, ht;
+        int mt = fast_divmod(tile, p.fd_ntiles, &nt);
+        mt = fast_divmod(mt, p.fd_tiles_w, &wt);
+        const int it = fast_divmod(mt, p.fd_tiles_h, &ht);
+        const int w0 = wt * p.TW, h0 = ht * p.TH, i0 = it * p.TN;
         const int n0 = nt * p.co_tile;
 
         const __nv_bfloat16* resrow = nullptr;
-        if (p.res) {
+        if (k_res) {
             const int w = w0 + tw, h = h0 + th, n = i0 + tn;
             if ((tn < p.TN) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo))
                 resrow = p.res + (((long long)n * p.Ho + h) * p.Wo + w) * p.res_cstride + p.res_coff;
@@ -254,25 +271,27 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
         if (leader && g == 0 && lt == 0) YL_STAMP(4);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.acc_stride);
 
-        for (int s = 0; s < p.nstore; ++s, ++kstore) {
+        for (int s = 0; s < nstore; ++s, ++kstore) {
             const uint32_t buf = dbl ? (kstore & 1u) * p.stg_bytes : 0u;
-            for (int u = 0; u < p.stg_sub; ++u) {
-                const int c = s * p.stg_sub + u;
-                if (c >= p.nchunks) break;
+            for (int u = 0; u < stg_sub; ++u) {
+                const int c = s * stg_sub + u;
+                if (c >= nchunks) break;
                 const int col0 = n0 + c * CW;  // first output channel of this chunk
                 uint32_t acc[CW];
                 tmem_ld_cw<CW>(taddr + (uint32_t)(c * CW), acc);
                 // residual rows are independent of the accumulator: issue the loads under the TMEM latency
                 uint4 rv[CW / 8];
+                if (k_res) {
 #pragma unroll
-                for (int i = 0; i < CW / 8; ++i) {
-                    rv[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (resrow && col0 + i * 8 < p.res_c)
-                        rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
+                    for (int i = 0; i < CW / 8; ++i) {
+                        rv[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (resrow && col0 + i * 8 < p.res_c)
+                            rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
+                    }
                 }
                 tmem_ld_wait();
                 if (leader && g == 0 && lt == 0 && c < 3) YL_STAMP(c == 0 ? 8 : (c == 1 ? 12 : 14));
-                if (c == p.nchunks - 1) {
+                if (c == nchunks - 1) {
                     // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -287,11 +306,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                     v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
                     v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
                 }
-                if (p.act) {
+                if (k_act) {
 #pragma unroll
                     for (int i = 0; i < CW; ++i) v[i] = silu_fast(v[i]);
                 }
-                if (p.res) {
+                if (k_res) {
 #pragma unroll
                     for (int i = 0; i < CW / 8; ++i) {
                         v[i * 8 + 0] += bf16lo_f(rv[i].x); v[i * 8 + 1] += bf16hi_f(rv[i].x);
@@ -300,11 +319,13 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                         v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
                     }
                 }
-                if (p.det_mode == YL_DET_CLS_FILTER)
-                    det_filter_chunk<CW>(p, v, c, w0 + row, lane, det_best, det_bestc);
-                else if (p.det_mode)
-                    det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
-                if (!p.store_y) continue;
+                if (GENERIC) {
+                    if (k_det == YL_DET_CLS_FILTER)
+                        det_filter_chunk<CW>(p, v, c, w0 + row, lane, det_best, det_bestc);
+                    else if (k_det)
+                        det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
+                }
+                if (!k_store) continue;
                 if (leader && g == 0 && lt == 0 && c < 2) YL_STAMP(c == 0 ? 9 : 13);
                 if (u == 0) {
                     // the staging tile about to be overwritten must have been drained by its last TMA store:
@@ -324,11 +345,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                     if (leader && g == 0 && lt == 0 && (c == 0 || c == 2)) YL_STAMP(c == 0 ? 10 : 15);
                 }
                 const uint32_t base_off = row_off + (uint32_t)u * sub_bytes;
-                if (p.y_f32) {
+                if (k_f32) {
 #pragma unroll
                     for (int j = 0; j < CW / 4; ++j) {
                         uint32_t off = base_off + (uint32_t)j * 16u;
-                        off ^= ((off >> 7) & swz_mask) << 4;
+                        off ^= ((off >> 7) & swz_mask) << 4;   // fp32 rows of 128 B: a chunk may start a new line
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + buf + off),
                                      "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
                                      : "memory");
@@ -336,8 +357,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                 } else {
 #pragma unroll
                     for (int j = 0; j < CW / 8; ++j) {
-                        uint32_t off = base_off + (uint32_t)j * 16u;
-                        off ^= ((off >> 7) & swz_mask) << 4;
+                        const uint32_t off = (base_off + (uint32_t)j * 16u) ^ swz_xor;
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + buf + off),
                                      "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
                                      "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
@@ -347,13 +367,13 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                     }
                 }
             }
-            if (!p.store_y) continue;
+            if (!k_store) continue;
             fence_proxy_async_smem();
             if (leader && g == 0 && lt == 0 && s == 0) YL_STAMP(11);
             if (dbl) {
                 pend = 1;
                 pbuf = buf;
-                pc0 = n0 + s * p.stg_sub * CW;
+                pc0 = n0 + s * stg_sub * CW;
                 pw0 = w0;
                 ph0 = h0;
                 pi0 = i0;
@@ -361,7 +381,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                 named_bar_sync(1 + g, kEpiGroupThreads);
                 if (leader) {
                     for (int m = p.y_map_first; m < p.y_map_last; ++m)
-                        tma_store_4d(&p.tmY[m], stg, n0 + s * p.stg_sub * CW, w0, h0, i0);
+                        tma_store_4d(&p.tmY[m], stg, n0 + s * stg_sub * CW, w0, h0, i0);
                     bulk_commit();
                 }
             }
@@ -384,6 +404,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
 // tile boundaries (the smem ring never drains), and with two TMEM accumulator stages the epilogue of tile i
 // overlaps the loads and MMAs of tiles i+1, i+2.
+template <bool DBG>
 __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // broadcast from lane 0 so the compiler treats the warp index (and every role / tile index derived from it)
@@ -478,11 +499,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         uint32_t ph = 0;  // ring position / phase of the stage being filled
         if (p.patch) {
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                int mt = tile;
-                const int w0 = (mt % p.tiles_w) * p.TW;
-                mt /= p.tiles_w;
-                const int h0 = (mt % p.tiles_h) * p.TH;
-                const int i0 = mt / p.tiles_h;
+                int wt, ht;
+                const int mt = fast_divmod(tile, p.fd_tiles_w, &wt);
+                const int i0 = fast_divmod(mt, p.fd_tiles_h, &ht);
+                const int w0 = wt * p.TW, h0 = ht * p.TH;
                 mbar_wait(&empty_bar[st], ph ^ 1u);
                 if (leader) {
                     mbar_expect_tx(&full_bar[st], p.tx_bytes);
@@ -495,12 +515,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
             }
         } else {
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
-                int mt = tile / p.n_tiles;
-                const int w0 = (mt % p.tiles_w) * p.TW;
-                mt /= p.tiles_w;
-                const int h0 = (mt % p.tiles_h) * p.TH;
-                const int i0 = (mt / p.tiles_h) * p.TN;
+                int nt, wt, ht;
+                int mt = fast_divmod(tile, p.fd_ntiles, &nt);
+                mt = fast_divmod(mt, p.fd_tiles_w, &wt);
+                const int it = fast_divmod(mt, p.fd_tiles_h, &ht);
+                const int w0 = wt * p.TW, h0 = ht * p.TH, i0 = it * p.TN;
                 const int n0 = nt * p.co_tile;
                 int tap = 0;
                 for (int r = 0; r < p.ksize; ++r) {
@@ -619,10 +638,16 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         const int gtid = (e & 3) * 32 + lane;
         uint8_t* stg = sStg + (size_t)g * p.stg_bufs * p.stg_bytes;
-        if (p.cw == 32)
-            conv_tc_epilogue<32>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
+        // epi_kind: 0 / 1 = the hot instantiations (32-column chunks, bf16 NHWC store, SiLU, without / with residual),
+        // 2 = every other combination
+        if (p.epi_kind == 0)
+            conv_tc_epilogue<32, true, false, false, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
+        else if (p.epi_kind == 1)
+            conv_tc_epilogue<32, true, true, false, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
+        else if (p.cw == 32)
+            conv_tc_epilogue<32, false, false, true, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
         else
-            conv_tc_epilogue<16>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
+            conv_tc_epilogue<16, false, false, true, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
     }
 
     tc_fence_before();
@@ -632,19 +657,25 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static unsigned long long* g_dbg_buf = nullptr;  // yl_debug_timeline: device buffer of [capacity][8] timestamps
-static int g_dbg_cap = 0, g_dbg_next = 0;
+// yl_debug_timeline: device buffer of [capacity][16] timestamps; state of the CALLING THREAD (the thread that arms it
+// is the one whose launches are stamped), so concurrent users of the library are unaffected
+static thread_local unsigned long long* g_dbg_buf = nullptr;
+static thread_local int g_dbg_cap = 0, g_dbg_next = 0;
 static int g_max_dyn_smem = 0;
 static int g_num_sms = 148;
 
+static void read_knobs();
+
 int init_conv_tc() {
+    read_knobs();
     int dev = 0;
     YL_CUDA(cudaGetDevice(&dev));
     int max_optin = 0;
     YL_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     g_max_dyn_smem = max_optin;
     YL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    YL_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    YL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    YL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return YL_OK;
 }
 
@@ -779,6 +810,30 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// Tuning knobs (A/B switches used by tools/): read from the environment ONCE, in yl_init; launches never touch getenv.
+struct ConvTcKnobs {
+    int nsplit = 1, patch = 1, patch_k64 = 0, patch_wmax_kb = 80, small_nsplit = 1, patch_pitch = 10, patch_bo = 0;
+    int wres = 1, stg_sub = 2, stg_bufs = 2, wearly = 1, grid_ctas = 2, patch_eff_pct = 60;
+};
+static ConvTcKnobs g_knobs;
+static void read_knobs() {
+    ConvTcKnobs k;
+    k.nsplit = env_int("YL_NSPLIT", k.nsplit);
+    k.patch = env_int("YL_PATCH", k.patch);
+    k.patch_k64 = env_int("YL_PATCH_K64", k.patch_k64);
+    k.patch_wmax_kb = env_int("YL_PATCH_WMAX_KB", k.patch_wmax_kb);
+    k.small_nsplit = env_int("YL_SMALL_NSPLIT", k.small_nsplit);
+    k.patch_pitch = env_int("YL_PATCH_PITCH", k.patch_pitch);
+    k.patch_bo = env_int("YL_PATCH_BO", k.patch_bo);
+    k.wres = env_int("YL_WRES", k.wres);
+    k.stg_sub = env_int("YL_STG_SUB", k.stg_sub);
+    k.stg_bufs = env_int("YL_STG_BUFS", k.stg_bufs);
+    k.wearly = env_int("YL_WEARLY", k.wearly);
+    k.grid_ctas = env_int("YL_GRID_CTAS", k.grid_ctas);
+    k.patch_eff_pct = env_int("YL_PATCH_EFF", k.patch_eff_pct);
+    g_knobs = k;
+}
+
 // Everything of a launch that is decided on the host: tiling, mode (flat / halo patch / resident weights / N split),
 // smem carve-up and the tensor maps.  Shared by the launch and by yl_conv_tc_info (tests assert which path ran).
 static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* smem_out) {
@@ -818,7 +873,7 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     {
         const long long m_est = ceil_div64((long long)x.n * Ho * Wo, 128);
         // (the class-filter epilogue needs every class of a pixel in ONE tile)
-        if (n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && env_int("YL_NSPLIT", 1) &&
+        if (n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && g_knobs.nsplit &&
             a->det.mode != YL_DET_CLS_FILTER)
             n_tiles = 2;
     }
@@ -827,13 +882,25 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     // halo-patch mode: 3x3 stride-1 convs on thin inputs are L2->SM bound when every tap is fetched separately
     // (9 narrow TMA boxes per tile); fetch the (TH+2) x (TW+2) patch once instead and slide the A descriptor
     bool patch = false;
-    if (a->k == 3 && a->stride == 1 && x.c <= 64 && n_tiles == 1 && env_int("YL_PATCH", 1)) {
-        const int kb = env_int("YL_PATCH_K64", 0) ? 64 : p.kblk;
+    if (a->k == 3 && a->stride == 1 && x.c <= 64 && n_tiles == 1 && g_knobs.patch) {
+        const int kb = g_knobs.patch_k64 ? 64 : p.kblk;
         const double eff = (double)Ho * Wo / ((double)ceil_div(Wo, 8) * 8 * ceil_div(Ho, 16) * 16);
-        if (9 * p.co_tile * kb * 2 <= env_int("YL_PATCH_WMAX_KB", 80) * 1024 && eff >= 0.6) {
+        if (9 * p.co_tile * kb * 2 <= g_knobs.patch_wmax_kb * 1024 && eff * 100.0 >= (double)g_knobs.patch_eff_pct) {
             patch = true;
             p.kblk = kb;
             p.cin_blocks = 1;
+        }
+    }
+    // Small problems (bs = 1 latency): with far fewer 128-pixel tiles than SMs a CTA's epilogue walks its N / 32 column
+    // chunks serially (~0.45 us each, tools/timeline.py) while most of the GPU idles.  Split N down to 32-column tiles:
+    // the chunks become parallel CTAs (the A tile is re-read from L2 by each, which is free at this size).
+    if (!patch && g_knobs.small_nsplit && (a->det.mode == YL_DET_NONE || a->det.mode == YL_DET_CLS)) {
+        const long long m_est = ceil_div64((long long)x.n * Ho * Wo, 128);
+        int nt = n_tiles;
+        while (m_est * nt * 2 <= g_num_sms && co16 % (64 * nt) == 0 && co16 / (2 * nt) >= 32) nt *= 2;
+        if (nt != n_tiles) {
+            n_tiles = nt;
+            p.co_tile = co16 / nt;
         }
     }
     const CUtensorMapSwizzle swp = swizzle_for_bytes(p.kblk * 2);
@@ -844,8 +911,8 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     const bool flat = (a->k == 1 && a->stride == 1 && !a->upsample2x && !a->y_up.data);
     if (patch) {
         p.patch = 1;
-        p.patch_pw = env_int("YL_PATCH_PITCH", 10);
-        p.patch_bo = env_int("YL_PATCH_BO", 0);  // measured: the swizzle XOR uses absolute smem address bits
+        p.patch_pw = g_knobs.patch_pitch;
+        p.patch_bo = g_knobs.patch_bo;  // measured: the swizzle XOR uses absolute smem address bits
         YL_CHECK(p.patch_pw >= 10 && p.patch_pw <= 16, YL_ERR_ARG, "YL_PATCH_PITCH must be in [10, 16]");
         p.Ho = Ho;
         p.Wo = Wo;
@@ -937,6 +1004,10 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.n_tiles = n_tiles;
     p.total_tiles = p.m_tiles * n_tiles;
+    YL_CHECK((long long)p.m_tiles * n_tiles < (1ll << 31), YL_ERR_ARG, "too many tiles");
+    p.fd_ntiles = make_fastdiv(n_tiles);
+    p.fd_tiles_w = make_fastdiv(p.tiles_w);
+    p.fd_tiles_h = make_fastdiv(p.tiles_h);
     // two accumulator stages (one per epilogue group); two CTAs per SM when TMEM and smem allow
     uint32_t cols = 32;
     while ((int)cols < 2 * p.acc_stride) cols <<= 1;
@@ -946,7 +1017,7 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     if (patch && p.b_bytes > 40u * 1024u) ctas_per_sm = 1;  // big resident 9-tap weights: one CTA owns the SM
     const int kiters_total = a->k * a->k * p.cin_blocks;
     const size_t wres_bytes = (size_t)kiters_total * p.b_bytes;
-    if (!patch && n_tiles == 1 && env_int("YL_WRES", 1) &&
+    if (!patch && n_tiles == 1 && g_knobs.wres &&
         wres_bytes <= (size_t)(ctas_per_sm == 2 ? 48 : 120) * 1024) {
         p.wres = 1;
         p.w_bytes = (uint32_t)kiters_total * (uint32_t)p.co_tile * p.kblk * 2u;
@@ -962,8 +1033,8 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     // too shallow to cover the HBM latency
     int sub_pref = (!p.y_f32 && p.cw == 32 && p.nchunks >= 2) ? 2 : 1;
     if (n_tiles > 1 && (p.nchunks & 1)) sub_pref = 1;  // a half-filled store row would spill into the next N tile
-    sub_pref = env_int("YL_STG_SUB", sub_pref) >= 2 ? sub_pref : 1;
-    const int bufs_pref = env_int("YL_STG_BUFS", 2) >= 2 ? 2 : 1;
+    sub_pref = g_knobs.stg_sub >= 2 ? sub_pref : 1;
+    const int bufs_pref = g_knobs.stg_bufs >= 2 ? 2 : 1;
     const int cand[4][2] = {{sub_pref, bufs_pref}, {1, bufs_pref}, {sub_pref, 1}, {1, 1}};
     size_t fixed = 0;
     int stages = 0;
@@ -1023,7 +1094,7 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
                 reinterpret_cast<char*>(a->det.cand_ws) + ((size_t)x.n * 4 + 255) / 256 * 256);
         }
     }
-    p.wearly = env_int("YL_WEARLY", 1);
+    p.wearly = g_knobs.wearly;
     p.bias = a->bias;
     p.n_bias = a->co_pad;
     p.act = a->act;
@@ -1031,8 +1102,9 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     p.res_cstride = a->res.cstride;
     p.res_coff = a->res.coff;
     p.res_c = a->res.c;
+    p.epi_kind = (p.cw == 32 && !p.y_f32 && p.store_y && !p.det_mode && p.act) ? (p.res ? 1 : 0) : 2;
 
-    int grid = g_num_sms * (ctas_per_sm < env_int("YL_GRID_CTAS", 2) ? ctas_per_sm : env_int("YL_GRID_CTAS", 2));
+    int grid = g_num_sms * (ctas_per_sm < g_knobs.grid_ctas ? ctas_per_sm : g_knobs.grid_ctas);
     if (grid > p.total_tiles) grid = p.total_tiles;
     *grid_out = grid;
     *smem_out = smem;
@@ -1045,8 +1117,12 @@ int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {
     size_t smem = 0;
     const int rc = plan_conv_tc(a, p, &grid, &smem);
     if (rc != YL_OK) return rc;
-    if (g_dbg_buf && g_dbg_next < g_dbg_cap) p.dbg = g_dbg_buf + 16ll * g_dbg_next++;
-    YL_CUDA(launch_kernel(conv_tc_kernel, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
+    if (g_dbg_buf && g_dbg_next < g_dbg_cap) {
+        p.dbg = g_dbg_buf + 16ll * g_dbg_next++;
+        YL_CUDA(launch_kernel(conv_tc_kernel<true>, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
+    } else {
+        YL_CUDA(launch_kernel(conv_tc_kernel<false>, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
+    }
     YL_LAUNCH_OK("conv_tc_kernel");
     return YL_OK;
 }

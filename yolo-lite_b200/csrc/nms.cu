@@ -18,6 +18,7 @@
 // IoU arithmetic follows torchvision's CPU kernel operation by operation (no FMA contraction, same
 // std::max/std::min operand order, fp32 IoU compared against the double threshold).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -143,6 +144,7 @@ struct SelParams {
     float max_wh;        // class offset scale (0 when agnostic)
     int max_det, max_nms;
     int kept_in_smem;
+    int classwise;       // allow the per-class path (A/B switch YL_NMS_CLASSWISE, default on)
     float* kept_ws;      // global kept-list storage when max_det is large: [B][max_det][5] + keys
     unsigned long long* kept_keys_ws;
     float* out;          // MODE 0: (B, max_det, 6)
@@ -242,6 +244,175 @@ __device__ __forceinline__ int key_bin(unsigned long long k) {
     return (kBins - 1) - b;
 }
 
+
+// ---------------------------------------------------------------------------------------------- class-wise select
+// With class offsets (ops.py:258, 264: boxes + cls * max_wh) two boxes of DIFFERENT classes cannot overlap as long as
+// the x extent of all candidates of the image is shorter than max_wh: their offset x intervals are then disjoint, so
+// inter == 0 and torchvision's `iou > thr` is false whatever the boxes are.  Greedy NMS over the whole list is then
+// exactly one independent greedy NMS per class followed by a merge of the survivors in score order — the O(n^2) pairwise
+// work shrinks by the number of classes and the serial dependency chains become one short chain per class, resolved by
+// different warps in parallel.  Taken when the image has at most kCwCap candidates, no class more than kCwMaxSeg of
+// them, and the extent test holds; everything else (agnostic NMS, max_nms cuts, huge candidate lists) runs the general
+// path below.  Both paths produce identical results (the arithmetic per pair is the same function).
+constexpr int kCwCap = 4096;
+constexpr int kCwMaxSeg = 256;
+
+__device__ __forceinline__ bool select_classwise(const SelParams& p, int b, int n, const unsigned long long* gkeys,
+                                                 unsigned char* sm, unsigned long long* kept_keys, int* nk_out) {
+    // the 128 KB key area of the general path, re-carved: sort keys | offset boxes | areas | keep flags
+    unsigned long long* key2 = reinterpret_cast<unsigned long long*>(sm);                    // [kCwCap]    32 KB
+    float4* obox = reinterpret_cast<float4*>(key2 + kCwCap);                                 // [kCwCap]    64 KB
+    float* oarea = reinterpret_cast<float*>(obox + kCwCap);                                  // [kCwCap]    16 KB
+    unsigned char* keepflag = reinterpret_cast<unsigned char*>(oarea + kCwCap);              // [kCwCap]     4 KB
+    int* seg_s = reinterpret_cast<int*>(keepflag + kCwCap);                                  // [1024]       4 KB
+    int* seg_e = seg_s + 1024;                                                               // [1024]       4 KB
+    unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(sm + (size_t)kSortCap * 8);   // [4096] (mask area)
+    int* misc = reinterpret_cast<int*>(sm + (size_t)kSortCap * 8 + (size_t)kChunk * kMaskWords * 4 +
+                                       (size_t)kChunk * (16 + 4 + 4) + 256 * 4);             // [64]
+    float* red = reinterpret_cast<float*>(sm + (size_t)kSortCap * 8 + (size_t)kChunk * kMaskWords * 4);   // [64] (cbox area)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nc = (uint32_t)p.nc;
+
+    // ---- 1. keys regrouped as (class | descending score | anchor): one sort gives per-class score order
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += kSelThreads) {
+        unsigned long long k2 = ~0ull;
+        if (i < n) {
+            const unsigned long long k = gkeys[i];
+            const uint32_t idx = (uint32_t)(k & 0xffffffffull);
+            const uint32_t a = idx / nc, c = idx - a * nc;
+            k2 = ((unsigned long long)c << 54) | ((k >> 32) << 22) | (unsigned long long)a;
+        }
+        key2[i] = k2;
+        if (i < kCwCap) keepflag[i] = 0;
+    }
+    for (int i = tid; i < 1024; i += kSelThreads) {
+        seg_s[i] = 0;
+        seg_e[i] = 0;
+    }
+    if (tid == 0) {
+        misc[0] = 0;   // fallback flag
+        misc[1] = 0;   // kept counter
+    }
+    __syncthreads();
+    block_bitonic_sort(key2, P, tid);
+
+    // ---- 2. boxes of the sorted candidates, class segments, extent of the raw x coordinates
+    float xmin = INFINITY, xmax = -INFINITY;
+    bool bad = false;
+    for (int i = tid; i < n; i += kSelThreads) {
+        const unsigned long long k2 = key2[i];
+        const uint32_t c = (uint32_t)(k2 >> 54), a = (uint32_t)(k2 & 0x3fffffull);
+        const unsigned long long k = (((k2 >> 22) & 0xffffffffull) << 32) | (unsigned long long)(a * nc + c);
+        float4 rb, ob;
+        float ar, sc;
+        int cl;
+        fetch_box<0>(p, b, k, &rb, &ob, &ar, &sc, &cl);
+        obox[i] = ob;
+        oarea[i] = ar;
+        if (!(rb.x == rb.x) || !(rb.z == rb.z)) bad = true;   // NaN: the extent argument does not apply
+        xmin = fminf(xmin, fminf(rb.x, rb.z));
+        xmax = fmaxf(xmax, fmaxf(rb.x, rb.z));
+        const uint32_t cprev = i > 0 ? (uint32_t)(key2[i - 1] >> 54) : 0xffffffffu;
+        const uint32_t cnext = i + 1 < n ? (uint32_t)(key2[i + 1] >> 54) : 0xffffffffu;
+        if (c != cprev) seg_s[c] = i;
+        if (c != cnext) {
+            seg_e[c] = i + 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    }
+    if (lane == 0) {
+        red[warp] = xmin;
+        red[32 + warp] = xmax;
+    }
+    if (bad) misc[0] = 1;
+    __syncthreads();
+    if (tid < 32) {
+        float lo = red[tid], hi = red[32 + tid];
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        // offset intervals of different classes are disjoint iff the raw extent is shorter than the class pitch
+        if (tid == 0 && !(hi - lo < p.max_wh)) misc[0] = 1;
+    }
+    for (int c = tid; c < (int)nc; c += kSelThreads)
+        if (seg_e[c] - seg_s[c] > kCwMaxSeg) misc[0] = 1;
+    __syncthreads();
+    if (misc[0]) return false;   // (uniform) the general path redoes the image from the global keys
+
+    // ---- 3. one greedy NMS per class, classes spread over the warps
+    const IouThr thr = {p.thr, p.thr_mid, p.thr_tie_up};
+    for (int c = warp; c < (int)nc; c += kSelThreads / 32) {
+        const int s0 = seg_s[c], len = seg_e[c] - s0;
+        int kc = 0;   // kept of this class (a class cannot place more than max_det boxes in the final list)
+        for (int q0 = 0; q0 < len && kc < p.max_det; q0 += 32) {
+            const int j = q0 + lane;
+            const bool valid = j < len;
+            const float4 bj = valid ? obox[s0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float aj = valid ? oarea[s0 + j] : 0.f;
+            bool alive = valid;
+            // against the boxes of this class kept in earlier blocks (better scores)
+            for (int t = 0; t < q0; ++t) {
+                if (!keepflag[s0 + t]) continue;                       // uniform: one shared byte
+                if (alive && iou_suppresses(obox[s0 + t], oarea[s0 + t], bj, aj, thr)) alive = false;
+                if (!__any_sync(0xffffffffu, alive)) break;
+            }
+            // inside the block: row i = the candidates box i would suppress
+            const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+            uint32_t rowbits = 0;
+            for (int i = 0; i < 32; ++i) {
+                if (!((alive_mask >> i) & 1u)) continue;               // uniform
+                float4 bi;
+                bi.x = __shfl_sync(0xffffffffu, bj.x, i);
+                bi.y = __shfl_sync(0xffffffffu, bj.y, i);
+                bi.z = __shfl_sync(0xffffffffu, bj.z, i);
+                bi.w = __shfl_sync(0xffffffffu, bj.w, i);
+                const float ai = __shfl_sync(0xffffffffu, aj, i);
+                const bool sup = alive && lane > i && iou_suppresses(bi, ai, bj, aj, thr);
+                const uint32_t bits = __ballot_sync(0xffffffffu, sup);
+                if (lane == i) rowbits = bits;
+            }
+            uint32_t live = alive_mask, keep = 0;
+            int room = p.max_det - kc;
+            while (live && room > 0) {
+                const int l = __ffs(live) - 1;
+                keep |= 1u << l;
+                --room;
+                live &= ~(__shfl_sync(0xffffffffu, rowbits, l) | (1u << l));
+            }
+            if (valid && ((keep >> lane) & 1u)) keepflag[s0 + j] = 1;
+            kc += __popc(keep);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. survivors of all classes back in global score order; the best max_det are the result (ops.py:266)
+    for (int i = tid; i < n; i += kSelThreads) {
+        if (!keepflag[i]) continue;
+        const unsigned long long k2 = key2[i];
+        const uint32_t c = (uint32_t)(k2 >> 54), a = (uint32_t)(k2 & 0x3fffffull);
+        kbuf[atomicAdd(&misc[1], 1)] = (((k2 >> 22) & 0xffffffffull) << 32) | (unsigned long long)(a * nc + c);
+    }
+    __syncthreads();
+    const int K = misc[1];
+    int P2 = 32;
+    while (P2 < K) P2 <<= 1;
+    for (int i = K + tid; i < P2; i += kSelThreads) kbuf[i] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort(kbuf, P2, tid);
+    const int nk = K < p.max_det ? K : p.max_det;
+    for (int r = tid; r < nk; r += kSelThreads) kept_keys[r] = kbuf[r];
+    __syncthreads();
+    *nk_out = nk;
+    return true;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -270,6 +441,12 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
 
     int nk = 0;          // kept so far (uniform across the block)
     int processed = 0;   // candidates consumed in sorted order
+    // per-class greedy NMS when the class offsets provably separate the classes (see select_classwise)
+    bool classwise_done = false;
+    if (MODE == 0 && p.classwise && p.max_wh > 0.f && n >= 1 && n <= kCwCap && n <= p.max_nms && p.nc <= 1024 &&
+        p.A < (1 << 22) && p.kept_in_smem)
+        classwise_done = select_classwise(p, b, n, gkeys, sm, kept_keys, &nk);
+    __syncthreads();
     unsigned long long lo = 0;  // keys <= lo are already consumed (radix rounds)
     const bool single_round = n <= kDirectSort;
     // bin mode: cumulative histogram of the coarse score bins (lives in the tail of the key buffer)
@@ -316,7 +493,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
         __syncthreads();
     }
 
-    while (processed < n_proc && nk < p.max_det) {
+    while (!classwise_done && processed < n_proc && nk < p.max_det) {
         int m = n_proc - processed;
         if (m > kSortCap) m = kSortCap;
         int consumed = m;  // candidates this round removes from the unprocessed set
@@ -591,8 +768,13 @@ static size_t sel_smem_bytes(int max_det, bool kept_in_smem) {
 }
 
 static int g_sel_max_smem = 0;
+static int g_nms_classwise = 1;   // YL_NMS_CLASSWISE, read once in yl_init
 
 int init_nms() {
+    {
+        const char* e = getenv("YL_NMS_CLASSWISE");
+        g_nms_classwise = (e && *e) ? (atoi(e) != 0) : 1;
+    }
     int dev = 0;
     YL_CUDA(cudaGetDevice(&dev));
     YL_CUDA(cudaDeviceGetAttribute(&g_sel_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -667,6 +849,7 @@ static int launch_select(const float* pred, int B, int nc, int A, size_t cap, co
     p.max_det = max_det;
     p.max_nms = max_nms;
     p.kept_in_smem = 1;
+    p.classwise = g_nms_classwise;
     p.kept_ws = nullptr;
     p.kept_keys_ws = nullptr;
     p.out = out;
@@ -792,6 +975,7 @@ int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thre
     p.max_det = n;
     p.max_nms = n;
     p.kept_in_smem = 0;
+    p.classwise = 0;
     p.kept_ws = kept_ws;
     p.kept_keys_ws = kept_keys_ws;
     p.out = nullptr;

@@ -26,16 +26,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 EncodeTiledFn get_encode_tiled() { return g_encode; }
 
-static int g_pdl_env = -1;   // YL_PDL environment switch (default on)
-static int g_pdl_user = 1;   // yl_set_pdl()
+static int g_pdl_env = 1;                 // YL_PDL environment switch, read once in yl_init (default on)
+static thread_local int t_pdl_user = 1;   // yl_set_pdl(): a launch attribute of the CALLING THREAD, like the current device
 
-bool pdl_enabled() {
-    if (g_pdl_env < 0) {
-        const char* e = getenv("YL_PDL");
-        g_pdl_env = (e && *e) ? (atoi(e) != 0) : 1;
-    }
-    return g_pdl_env != 0 && g_pdl_user != 0;
-}
+bool pdl_enabled() { return g_pdl_env != 0 && t_pdl_user != 0; }
 
 int init_conv_tc();    // conv_tc.cu
 int init_nms();        // nms.cu
@@ -52,8 +46,8 @@ extern "C" {
 int yl_version(void) { return YL11_VERSION; }
 
 int yl_set_pdl(int enabled) {
-    const int prev = yl::g_pdl_user;
-    yl::g_pdl_user = enabled ? 1 : 0;
+    const int prev = yl::t_pdl_user;
+    yl::t_pdl_user = enabled ? 1 : 0;
     return prev;
 }
 
@@ -81,6 +75,10 @@ int yl_init(int device) {
         YL_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, YL_ERR_CUDA,
                  "cuTensorMapEncodeTiled not available from the driver");
         yl::g_encode = reinterpret_cast<yl::EncodeTiledFn>(fn);
+    }
+    {
+        const char* e = getenv("YL_PDL");
+        yl::g_pdl_env = (e && *e) ? (atoi(e) != 0) : 1;
     }
     int rc;
     if ((rc = yl::init_conv_tc()) != 0) return rc;
