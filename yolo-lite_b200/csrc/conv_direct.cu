@@ -611,11 +611,18 @@ constexpr int kStemPatchCols = 2 * kStemRowPixels + 4;
 
 // K order: k = tap * 4 + ci (ci padded to 4), K = 36 -> 3 k-steps of 16.
 template <int CO, int CI>
-__global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
+__global__ void __launch_bounds__(32 * kStemWarps, 3) stem_conv_kernel(
     const float* __restrict__ x, int N, int H, int W, const __nv_bfloat16* __restrict__ wp, int ci_pad,
     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long y_cstride, int y_coff, int Ho, int Wo,
     int act) {
-    constexpr int NT = CO / 8;
+    // Output channels are processed in passes of NTP n-tiles (<= 32 channels): the stationary weight fragments, biases
+    // and accumulators of ALL 64 / 96 channels cost 144 registers, i.e. one block of 8 warps per SM (ncu: 12 % of the
+    // warp slots busy, the staging barrier fully exposed).  A pass re-reads its A fragments from the staged patch
+    // (shared-memory bandwidth is plentiful here) and keeps the kernel at <= 80 registers = 3 blocks per SM.
+    constexpr int NT_ALL = CO / 8;
+    constexpr int NT = NT_ALL <= 4 ? NT_ALL : ((NT_ALL % 4 == 0) ? 4 : 2);
+    constexpr int PASSES = NT_ALL / NT;
+    static_assert(NT_ALL % NT == 0, "pass width must divide the channel count");
     constexpr int KSTEPS = 3;
     constexpr int Ci = CI;
     __shared__ __align__(16) uint2 patch[kStemPatchRows * kStemPatchCols];  // one pixel = 4 x bf16 = 8 bytes
@@ -630,9 +637,10 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
     // B fragments: b0 = {W[k0][n], W[k0+1][n]}, b1 = {W[k0+8][n], W[k0+9][n]}, k0 = 16*ks + 2t, n = 8*nt + g
     uint32_t bfrag[KSTEPS][NT][2];
     float bia[NT][2];
+    auto load_weights = [&](int pass) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int co = nt * 8 + g;
+        const int co = (pass * NT + nt) * 8 + g;
         const __nv_bfloat16* wrow = wp + (long long)co * 9 * ci_pad;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks)
@@ -649,9 +657,11 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
                 }
                 bfrag[ks][nt][hh] = v;
             }
-        bia[nt][0] = __ldg(bias + nt * 8 + 2 * t);
-        bia[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+        bia[nt][0] = __ldg(bias + (pass * NT + nt) * 8 + 2 * t);
+        bia[nt][1] = __ldg(bias + (pass * NT + nt) * 8 + 2 * t + 1);
     }
+    };
+    load_weights(0);
     griddep_wait();
 
     // ---- stage the patch: a work item = 4 consecutive columns of one patch row, all channels (coalesced 16-B
@@ -714,6 +724,11 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
     __nv_bfloat16* yrow = y + ((long long)n * Ho + ho) * Wo * y_cstride + y_coff;
 
 #pragma unroll 1
+    for (int pass_ = 0; pass_ < PASSES; ++pass_) {
+    int pass = pass_;
+    asm volatile("" : "+r"(pass));   // opaque: keeps a 2-pass loop from being unrolled back into one 144-register body
+    if (pass > 0) load_weights(pass);
+#pragma unroll 1
     for (int mt = 0; mt < kStemRowPixels / 16; ++mt) {
         const int wl0 = mt * 16;
         if (w0 + wl0 >= Wo) break;
@@ -740,7 +755,7 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
         // channels at once and a quad writes 2 x 32 contiguous bytes instead of sixteen scattered 4-byte stores
         const int swo = w0 + wl0 + g + 8 * (t >> 1);
         const bool st_ok = swo < Wo;
-        __nv_bfloat16* dst = yrow + (long long)swo * y_cstride + 8 * (t & 1);
+        __nv_bfloat16* dst = yrow + (long long)swo * y_cstride + pass * NT * 8 + 8 * (t & 1);
 #pragma unroll
         for (int np = 0; np < NT / 2; ++np) {
             float e[2][4];
@@ -762,6 +777,7 @@ __global__ void __launch_bounds__(32 * kStemWarps) stem_conv_kernel(
             }
             if (st_ok) *reinterpret_cast<uint4*>(dst + np * 16) = make_uint4(v0, v1, v2, v3);
         }
+    }
     }
 }
 

@@ -164,12 +164,12 @@ __device__ __forceinline__ void det_filter_chunk(const ConvTcParams& p, const fl
 
 template <int CW>
 __device__ __forceinline__ void det_decode_chunk(const ConvTcParams& p, const float (&v)[CW], int c, long long m,
-                                                 float (&dist)[4]) {
+                                                 float (&dist)[4], int det_mode) {
     if (m >= p.det_M) return;
     const int b = (int)(m / p.det_hw);
     const int al = (int)(m - (long long)b * p.det_hw);
     float* out = p.det_pred + (long long)b * (4 + p.det_nc) * p.det_A + p.det_anchor0 + al;
-    if (p.det_mode == YL_DET_BOX) {
+    if (det_mode == YL_DET_BOX) {
         if (CW == 32) {  // reg_max == 16: two sides per chunk
             float d2[2];
 #pragma unroll
@@ -219,15 +219,18 @@ __device__ __forceinline__ void det_decode_chunk(const ConvTcParams& p, const fl
 // ACT / RES): ncu showed ~300 warp instructions per 32-column chunk of which only ~160 were the math, the rest runtime
 // flag tests, parameter reloads, swizzle arithmetic and the (disabled) timeline stamps.  GENERIC == true keeps every
 // runtime option (fp32 destination, Detect decode / class filter, no NHWC store).
-template <int CW, bool ACT, bool RES, bool GENERIC, bool DBG>
+// DET (non-generic): 0 = plain bf16 NHWC store; YL_DET_BOX / YL_DET_CLS / YL_DET_CLS_FILTER = the engine path's head
+// convs, whose result feeds the fused Detect epilogue only (no NHWC store at all).
+template <int CW, bool ACT, bool RES, int DET, bool GENERIC, bool DBG>
 __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, int q, int lane, int gtid,
                                                  uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                  uint8_t* stg, const float* sbias) {
     const bool k_act = GENERIC ? (p.act != 0) : ACT;
     const bool k_res = GENERIC ? (p.res != nullptr) : RES;
     const bool k_f32 = GENERIC ? (p.y_f32 != 0) : false;
-    const int k_det = GENERIC ? p.det_mode : 0;
-    const bool k_store = GENERIC ? (p.store_y != 0) : true;
+    const int k_det = GENERIC ? p.det_mode : DET;
+    const bool k_store = GENERIC ? (p.store_y != 0) : (DET == 0);
+    const float bscale = k_act ? 0.5f : 1.0f;   // see the bias staging in the kernel prologue
     const int row = q * 32 + lane;
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
@@ -297,18 +300,21 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[g]);
                 }
+                // SiLU(x) = h + h * tanh(h) with h = x / 2 (one MUFU op).  For activated convs the staged bias is b / 2 and
+                // the accumulator is scaled by 1/2 in the same FMA: h = fma(acc, 0.5, b / 2) is bit-identical to
+                // 0.5 * (acc + b) (a scaling by two commutes with the rounding) and saves an instruction per element.
                 float v[CW];
 #pragma unroll
                 for (int i = 0; i < CW; i += 4) {
                     const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + i);
-                    v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
-                    v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
-                    v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
-                    v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+                    v[i + 0] = fmaf(__uint_as_float(acc[i + 0]), bscale, b.x);
+                    v[i + 1] = fmaf(__uint_as_float(acc[i + 1]), bscale, b.y);
+                    v[i + 2] = fmaf(__uint_as_float(acc[i + 2]), bscale, b.z);
+                    v[i + 3] = fmaf(__uint_as_float(acc[i + 3]), bscale, b.w);
                 }
                 if (k_act) {
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = silu_fast(v[i]);
+                    for (int i = 0; i < CW; ++i) v[i] = fmaf(v[i], tanh_approx(v[i]), v[i]);
                 }
                 if (k_res) {
 #pragma unroll
@@ -319,11 +325,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, i
                         v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
                     }
                 }
-                if (GENERIC) {
+                if (GENERIC || DET != 0) {
                     if (k_det == YL_DET_CLS_FILTER)
                         det_filter_chunk<CW>(p, v, c, w0 + row, lane, det_best, det_bestc);
                     else if (k_det)
-                        det_decode_chunk<CW>(p, v, c, w0 + row, det_dist);
+                        det_decode_chunk<CW>(p, v, c, w0 + row, det_dist, k_det);
                 }
                 if (!k_store) continue;
                 if (leader && g == 0 && lt == 0 && c < 2) YL_STAMP(c == 0 ? 9 : 13);
@@ -451,7 +457,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         tma_prefetch_desc(&p.tmB);
         if (p.store_y) tma_prefetch_desc(&p.tmY[p.y_map_first]);
     }
-    for (int i = threadIdx.x; i < nbias; i += blockDim.x) sbias[i] = i < p.n_bias ? __ldg(p.bias + i) : 0.f;
+    {
+        const float bs = p.act ? 0.5f : 1.0f;   // activated convs stage b / 2 (the epilogue works on h = x / 2)
+        for (int i = threadIdx.x; i < nbias; i += blockDim.x) sbias[i] = i < p.n_bias ? bs * __ldg(p.bias + i) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -640,14 +649,23 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         uint8_t* stg = sStg + (size_t)g * p.stg_bufs * p.stg_bytes;
         // epi_kind: 0 / 1 = the hot instantiations (32-column chunks, bf16 NHWC store, SiLU, without / with residual),
         // 2 = every other combination
-        if (p.epi_kind == 0)
-            conv_tc_epilogue<32, true, false, false, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
-        else if (p.epi_kind == 1)
-            conv_tc_epilogue<32, true, true, false, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
-        else if (p.cw == 32)
-            conv_tc_epilogue<32, false, false, true, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
-        else
-            conv_tc_epilogue<16, false, false, true, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias);
+        // epi_kind (host side, plan_conv_tc): the hot combinations get their own instantiation (32-column chunks):
+        //   0 / 1  SiLU, bf16 store, without / with residual        2 / 3  no activation, bf16 store, without / with residual
+        //   4 / 5 / 6  Detect box decode / class decode / class filter WITHOUT an NHWC store (engine path head convs)
+        //   7  everything else (fp32 destination, decode + raw store, 16-column chunks)
+#define YL_EPI(CW_, ACT_, RES_, DET_, GEN_) \
+    conv_tc_epilogue<CW_, ACT_, RES_, DET_, GEN_, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias)
+        const int kind = DBG ? 7 : p.epi_kind;     // the timeline build keeps only the generic code
+        if (kind == 0) YL_EPI(32, true, false, 0, false);
+        else if (kind == 1) YL_EPI(32, true, true, 0, false);
+        else if (kind == 2) YL_EPI(32, false, false, 0, false);
+        else if (kind == 3) YL_EPI(32, false, true, 0, false);
+        else if (kind == 4) YL_EPI(32, false, false, YL_DET_BOX, false);
+        else if (kind == 5) YL_EPI(32, false, false, YL_DET_CLS, false);
+        else if (kind == 6) YL_EPI(32, false, false, YL_DET_CLS_FILTER, false);
+        else if (p.cw == 32) YL_EPI(32, false, false, 0, true);
+        else YL_EPI(16, false, false, 0, true);
+#undef YL_EPI
     }
 
     tc_fence_before();
@@ -1102,7 +1120,11 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     p.res_cstride = a->res.cstride;
     p.res_coff = a->res.coff;
     p.res_c = a->res.c;
-    p.epi_kind = (p.cw == 32 && !p.y_f32 && p.store_y && !p.det_mode && p.act) ? (p.res ? 1 : 0) : 2;
+    p.epi_kind = 7;
+    if (p.cw == 32 && !p.y_f32 && p.store_y && !p.det_mode)
+        p.epi_kind = (p.act ? 0 : 2) + (p.res ? 1 : 0);
+    else if (p.cw == 32 && !p.store_y && !p.act && !p.res && p.det_mode)
+        p.epi_kind = p.det_mode == YL_DET_BOX ? 4 : (p.det_mode == YL_DET_CLS ? 5 : 6);
 
     int grid = g_num_sms * (ctas_per_sm < g_knobs.grid_ctas ? ctas_per_sm : g_knobs.grid_ctas);
     if (grid > p.total_tiles) grid = p.total_tiles;
