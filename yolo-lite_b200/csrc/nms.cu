@@ -145,6 +145,7 @@ struct SelParams {
     int max_det, max_nms;
     int kept_in_smem;
     int classwise;       // allow the per-class path (A/B switch YL_NMS_CLASSWISE, default on)
+    int first_chunk;     // size of the first greedy chunk (YL_NMS_CHUNK0, default 64; kChunk = fixed 512-candidate chunks)
     float* kept_ws;      // global kept-list storage when max_det is large: [B][max_det][5] + keys
     unsigned long long* kept_keys_ws;
     float* out;          // MODE 0: (B, max_det, 6)
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
         __syncthreads();
     }
 
+    int chunk = p.first_chunk;   // candidates per greedy chunk (grows up to kChunk)
     while (!classwise_done && processed < n_proc && nk < p.max_det) {
         int m = n_proc - processed;
         if (m > kSortCap) m = kSortCap;
@@ -627,8 +629,12 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
 
         // ---------------- greedy suppression over skeys[0..m) in chunks
         const IouThr thr = {p.thr, p.thr_mid, p.thr_tie_up};
-        for (int s0 = 0; s0 < m && nk < p.max_det; s0 += kChunk) {
-            const int cnt = (m - s0) < kChunk ? (m - s0) : kChunk;
+        // Chunks grow 64 -> 128 -> 256 -> 512: the pairwise test among a chunk's survivors is speculative work (most of a
+        // dense blob is suppressed by the first few kept boxes), so the first chunks are kept small; once there are kept
+        // boxes, step 1 prunes a chunk before the quadratic step sees it.
+        for (int s0 = 0, cnt = 0; s0 < m && nk < p.max_det; s0 += cnt) {
+            cnt = (m - s0) < chunk ? (m - s0) : chunk;
+            if (chunk < kChunk) chunk <<= 1;
             // 1. candidate vs kept list: two threads per candidate, each scanning every other kept box
             const int ci = tid >> 1, half = tid & 1;
             float4 ob = make_float4(0, 0, 0, 0), rb;
@@ -769,11 +775,16 @@ static size_t sel_smem_bytes(int max_det, bool kept_in_smem) {
 
 static int g_sel_max_smem = 0;
 static int g_nms_classwise = 1;   // YL_NMS_CLASSWISE, read once in yl_init
+static int g_nms_chunk0 = 64;     // YL_NMS_CHUNK0
 
 int init_nms() {
     {
         const char* e = getenv("YL_NMS_CLASSWISE");
         g_nms_classwise = (e && *e) ? (atoi(e) != 0) : 1;
+        const char* c0 = getenv("YL_NMS_CHUNK0");
+        int v = (c0 && *c0) ? atoi(c0) : 64;
+        g_nms_chunk0 = 32;
+        while (g_nms_chunk0 < v && g_nms_chunk0 < kChunk) g_nms_chunk0 <<= 1;
     }
     int dev = 0;
     YL_CUDA(cudaGetDevice(&dev));
@@ -850,6 +861,7 @@ static int launch_select(const float* pred, int B, int nc, int A, size_t cap, co
     p.max_nms = max_nms;
     p.kept_in_smem = 1;
     p.classwise = g_nms_classwise;
+    p.first_chunk = yl::g_nms_chunk0;
     p.kept_ws = nullptr;
     p.kept_keys_ws = nullptr;
     p.out = out;
@@ -976,6 +988,7 @@ int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thre
     p.max_nms = n;
     p.kept_in_smem = 0;
     p.classwise = 0;
+    p.first_chunk = yl::g_nms_chunk0;
     p.kept_ws = kept_ws;
     p.kept_keys_ws = kept_keys_ws;
     p.out = nullptr;
