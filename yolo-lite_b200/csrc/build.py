@@ -14,7 +14,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SOURCES = ["runtime.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "layout.cu", "pool.cu", "attention.cu",
-           "decode.cu", "nms.cu", "preprocess.cu", "c3k2_fused.cu", "stem_fused.cu", "metrics.cu"]
+           "decode.cu", "nms.cu", "preprocess.cu", "c3k2_fused.cu", "c3k2_tc.cu", "stem_fused.cu", "metrics.cu"]
 HEADERS = [HERE / "common.cuh", HERE.parents[1] / "include" / "yl11.h"]
 OUT_DIR = HERE.parent / "yololite" / "lib"
 LIB = OUT_DIR / "libyl11.so"

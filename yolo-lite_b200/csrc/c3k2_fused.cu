@@ -403,6 +403,13 @@ int init_c3k2() {
 
 }  // namespace yl
 
+namespace yl {
+bool c3k2_tc_supported(int c, int c2);
+int launch_c3k2_tc(const yl_tensor* t, const yl_tensor* y, const void* wa, const float* ba, int wa_ci_pad, const void* wb,
+                   const float* bb, int wb_ci_pad, const void* w2, const float* b2, int w2_ci_pad, int shortcut,
+                   cudaStream_t stream);
+}  // namespace yl
+
 extern "C" int yl_c3k2_tail_supported(int c, int c2) {
     return (c == 16 || c == 32) && (c2 == 32 || c2 == 64 || c2 == 128 || c2 == 256);
 }
@@ -424,6 +431,9 @@ extern "C" int yl_c3k2_tail(const yl_tensor* t, const yl_tensor* y, const void* 
              "packed weight layouts do not match the block (ci_pad %d / %d / %d for c = %d)", wa_ci_pad, wb_ci_pad,
              w2_ci_pad, c);
     YL_CHECK((long long)t->h * t->w < (1ll << 31), YL_ERR_ARG, "image too large");
+    // tcgen05 version (c3k2_tc.cu) for the shapes it is built for; the mma.sync kernel below covers the rest
+    if (yl::c3k2_tc_supported(c, y->c))
+        return yl::launch_c3k2_tc(t, y, wa, ba, wa_ci_pad, wb, bb, wb_ci_pad, w2, b2, w2_ci_pad, shortcut, (cudaStream_t)stream);
     yl::C3k2TailParams p;
     p.t = reinterpret_cast<const __nv_bfloat16*>(t->data);
     p.t_cstride = t->cstride;

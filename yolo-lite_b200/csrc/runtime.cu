@@ -36,6 +36,7 @@ int init_nms();        // nms.cu
 int init_attention();  // attention.cu
 int init_pool();       // pool.cu
 int init_c3k2();       // c3k2_fused.cu
+int init_c3k2_tc();    // c3k2_tc.cu
 int init_stem_fused(); // stem_fused.cu
 int init_metrics();    // metrics.cu
 
@@ -86,6 +87,7 @@ int yl_init(int device) {
     if ((rc = yl::init_attention()) != 0) return rc;
     if ((rc = yl::init_pool()) != 0) return rc;
     if ((rc = yl::init_c3k2()) != 0) return rc;
+    if ((rc = yl::init_c3k2_tc()) != 0) return rc;
     if ((rc = yl::init_stem_fused()) != 0) return rc;
     if ((rc = yl::init_metrics()) != 0) return rc;
     yl::g_device = device;
