@@ -207,6 +207,10 @@ int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, do
  * yl_nms_select runs the per-image sort + greedy suppression on the candidates found there.  `pred` needs valid box
  * rows only.  Same outputs, bit for bit, as yl_nms_batched(multi_label = 0, classes = NULL) on the full tensor. */
 int yl_nms_begin(void* workspace, size_t workspace_bytes, int B, void* stream);
+/* Debug aid (tools/nms_phases.py): subsequent select launches of the calling thread accumulate, per image, the clock
+ * cycles of their phases into device_buf[B][8] = {setup, round staging + sort, candidates vs kept, compaction, pairwise
+ * mask, serial resolve, kept, candidates consumed}.  NULL disables.  Not for production use. */
+int yl_debug_nms_phases(long long* device_buf);
 int yl_nms_select(const float* pred, int B, int nc, int A, double iou_thres, int agnostic, int max_det, int max_nms,
                   float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* counts, void* stream);
 size_t yl_nms_boxes_workspace_bytes(int n);

@@ -146,6 +146,7 @@ struct SelParams {
     int kept_in_smem;
     int classwise;       // allow the per-class path (A/B switch YL_NMS_CLASSWISE, default on)
     int first_chunk;     // size of the first greedy chunk (YL_NMS_CHUNK0, default 64; kChunk = fixed 512-candidate chunks)
+    long long* dbg;      // optional [B][8] phase cycle counters (tools/nms_phases.py); NULL in production
     float* kept_ws;      // global kept-list storage when max_det is large: [B][max_det][5] + keys
     unsigned long long* kept_keys_ws;
     float* out;          // MODE 0: (B, max_det, 6)
@@ -495,6 +496,16 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
     }
 
     int chunk = p.first_chunk;   // candidates per greedy chunk (grows up to kChunk)
+    long long tph = clock64(), acc_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define YL_PH(k)                                   \
+    do {                                           \
+        if (p.dbg && tid == 0) {                   \
+            const long long t_ = clock64();        \
+            acc_ph[k] += t_ - tph;                 \
+            tph = t_;                              \
+        }                                          \
+    } while (0)
+    YL_PH(0);
     while (!classwise_done && processed < n_proc && nk < p.max_det) {
         int m = n_proc - processed;
         if (m > kSortCap) m = kSortCap;
@@ -627,6 +638,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             }
         }
 
+        YL_PH(1);   // round staging: gather + sort
         // ---------------- greedy suppression over skeys[0..m) in chunks
         const IouThr thr = {p.thr, p.thr_mid, p.thr_tie_up};
         // Chunks grow 64 -> 128 -> 256 -> 512: the pairwise test among a chunk's survivors is speculative work (most of a
@@ -655,6 +667,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             // (the shuffle must be executed by every lane: no short-circuit in front of it)
             const int other_alive = __shfl_xor_sync(0xffffffffu, (int)alive, 1);
             alive = alive && other_alive && (half == 0);  // the even thread of the pair carries the candidate on
+            YL_PH(2);   // candidates vs kept
             // 2. ordered compaction of survivors
             const unsigned bal = __ballot_sync(0xffffffffu, alive);
             if (lane == 0) misc[8 + warp] = __popc(bal);
@@ -678,6 +691,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
                 csrc[pos] = s0 + ci;
             }
             __syncthreads();
+            YL_PH(3);   // compaction
             // 3. pairwise bitmask among survivors: only the words on or right of the diagonal exist.  A warp owns
             //    rows warp, warp+32, ... (every 32-row block gives each warp one row, so the triangle is balanced);
             //    its lanes take the 32 columns of one word: box j is read conflict-free, box i is a broadcast.
@@ -693,6 +707,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
                 }
             }
             __syncthreads();
+            YL_PH(4);   // pairwise mask
             // 4. resolve by warp 0, one block of 32 candidates at a time: the 32 x 32 diagonal block is resolved
             //    with register shuffles only (lane l holds row l's diagonal word), then the kept rows are OR-ed into
             //    the removed set (lane w owns word w) and appended to the kept list in parallel.
@@ -740,8 +755,14 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
             __syncthreads();
             nk = misc[4];
             __syncthreads();
+            YL_PH(5);   // serial resolve
         }
         processed += consumed;
+    }
+    if (p.dbg && tid == 0) {
+        acc_ph[6] = nk;
+        acc_ph[7] = processed;
+        for (int k = 0; k < 8; ++k) p.dbg[(long long)b * 8 + k] = acc_ph[k];
     }
 
     // ---------------- emit
@@ -776,6 +797,7 @@ static size_t sel_smem_bytes(int max_det, bool kept_in_smem) {
 static int g_sel_max_smem = 0;
 static int g_nms_classwise = 1;   // YL_NMS_CLASSWISE, read once in yl_init
 static int g_nms_chunk0 = 64;     // YL_NMS_CHUNK0
+static thread_local long long* g_nms_dbg = nullptr;   // yl_debug_nms_phases
 
 int init_nms() {
     {
@@ -862,6 +884,7 @@ static int launch_select(const float* pred, int B, int nc, int A, size_t cap, co
     p.kept_in_smem = 1;
     p.classwise = g_nms_classwise;
     p.first_chunk = yl::g_nms_chunk0;
+    p.dbg = yl::g_nms_dbg;
     p.kept_ws = nullptr;
     p.kept_keys_ws = nullptr;
     p.out = out;
@@ -924,6 +947,11 @@ int yl_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, do
 
     return yl::launch_select(pred, B, nc, A, cap, cand_counts, keys, iou_thres, agnostic, max_det, max_nms, max_wh, out,
                              counts, s);
+}
+
+int yl_debug_nms_phases(long long* device_buf) {
+    yl::g_nms_dbg = device_buf;
+    return YL_OK;
 }
 
 int yl_nms_begin(void* workspace, size_t workspace_bytes, int B, void* stream) {
@@ -989,6 +1017,7 @@ int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thre
     p.kept_in_smem = 0;
     p.classwise = 0;
     p.first_chunk = yl::g_nms_chunk0;
+    p.dbg = yl::g_nms_dbg;
     p.kept_ws = kept_ws;
     p.kept_keys_ws = kept_keys_ws;
     p.out = nullptr;

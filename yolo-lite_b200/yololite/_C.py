@@ -134,6 +134,7 @@ _PROTOTYPES = {
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "yl_nms_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "yl_debug_nms_phases": (C.c_int, [C.c_void_p]),
     "yl_nms_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yl_nms_boxes_workspace_bytes": (C.c_size_t, [C.c_int]),
