@@ -76,6 +76,34 @@ def test_coco8_rect_loader_matches_reference(real):
     np.testing.assert_allclose(b["bboxes"].numpy(), real["coco8.bboxes"], rtol=0, atol=2e-6)
 
 
+def _write_coco8_like(real, root):
+    """A coco8-style tree (images/val, labels/val, data yaml with a relative `path:`) from the fixture's JPEGs / labels."""
+    (root / "coco8" / "images" / "val").mkdir(parents=True)
+    (root / "coco8" / "labels" / "val").mkdir(parents=True)
+    for i, f in enumerate(real["coco8.files"]):
+        (root / "coco8" / "images" / "val" / str(f)).write_bytes(real[f"coco8.jpg{i}"].tobytes())
+        rows = real[f"coco8.txt{i}"].reshape(-1, 5)
+        (root / "coco8" / "labels" / "val" / (str(f).rsplit(".", 1)[0] + ".txt")).write_text(
+            "".join(f"{int(r[0])} {r[1]:.6g} {r[2]:.6g} {r[3]:.6g} {r[4]:.6g}\n" for r in rows))
+    y = root / "coco8.yaml"
+    y.write_text("path: coco8\ntrain: images/val\nval: images/val\nnames:\n" + "".join(f"  {i}: c{i}\n" for i in range(80)))
+    return y
+
+
+def test_val_loader_from_dataset_yaml(real, tmp_path):
+    """`YOLOLite.val(data=...)` route: the rect loader built from a dataset yaml (files on disk, YOLO txt labels) yields
+    the reference's batch: same image bytes (crc), same file order, labels within fp32 text round-off."""
+    from yololite.data import build_val_loader
+
+    loader, names = build_val_loader(_write_coco8_like(real, tmp_path), imgsz=640, batch_size=16, stride=32)
+    assert len(names) == 80 and len(loader) == 1
+    b = next(iter(loader))
+    assert zlib.crc32(b["img"].numpy().tobytes()) == int(real["coco8.img_crc"])
+    assert [p.rsplit("/", 1)[-1] for p in b["im_file"]] == [str(f) for f in real["coco8.files"]]
+    np.testing.assert_array_equal(b["cls"].numpy(), real["coco8.cls"])
+    np.testing.assert_allclose(b["bboxes"].numpy(), real["coco8.bboxes"], rtol=0, atol=5e-6)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _check_top_rows(y, real, tag):
     idx = torch.from_numpy(real[f"{tag}.top_idx"].astype(np.int64)).to(y.device)
@@ -212,5 +240,11 @@ def test_coco8_val_matches_reference(real):
     yl.model.cuda()
     metrics = yl.val(dataloader=[batch], device="cuda:0", verbose=False)
     keys = [str(k) for k in real["coco8.metric_keys"]]
+    import tempfile
+    from pathlib import Path
+
+    with tempfile.TemporaryDirectory() as td:       # the same through the dataset-yaml route
+        m2 = yl.val(data=str(_write_coco8_like(real, Path(td))), device="cuda:0", verbose=False)
+    assert m2.results_dict == metrics.results_dict
     for k, v in zip(keys, real["coco8.metric_vals"]):
         assert abs(float(metrics.results_dict[k]) - float(v)) <= 3e-3, (k, metrics.results_dict[k], v)   # 0.3 points

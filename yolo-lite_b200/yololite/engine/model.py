@@ -71,12 +71,23 @@ class YOLOLite(nn.Module):
         return self.predictor(source=source, stream=stream)
 
     def val(self, dataloader=None, **kwargs):
-        """Validate on labelled batches (reference engine/model.py val).  `dataloader`: iterable of batch dicts in
-        the reference's collate layout; building one from a dataset yaml is out of scope (see engine/validator.py)."""
+        """Validate on labelled batches (reference engine/model.py:101-107).  `dataloader`: iterable of batch dicts in
+        the reference's collate layout; or `data=<dataset yaml | image dir>`: the split is loaded with the minimal rect
+        loader (`yololite.data.RectValLoader`, the reference's `YOLODataset(rect=True)` batches)."""
         from .validator import DetectionValidator
 
         custom = {"rect": True}
         args = {**self.overrides, **custom, **kwargs, "mode": "val"}
+        if dataloader is None and kwargs.get("data"):
+            from ..data import build_val_loader
+
+            stride = int(self.model.stride.max()) if hasattr(self.model, "stride") else 32
+            imgsz = args.get("imgsz") or 640
+            dataloader, names = build_val_loader(kwargs["data"], imgsz=int(imgsz if isinstance(imgsz, int) else imgsz[0]),
+                                                 batch_size=int(args.get("batch") or 16), stride=max(stride, 32),
+                                                 split=args.get("split") or "val")
+            if names and len(names) == len(self.model.names):
+                self.model.names = dict(names) if isinstance(names, dict) else dict(enumerate(names))
         validator = DetectionValidator(dataloader=dataloader, args=args)
         validator(model=self.model)
         self.metrics = validator.metrics
