@@ -252,6 +252,13 @@ int yl_c3k2_tail_supported(int c, int c2);
 int yl_c3k2_tail(const yl_tensor* t, const yl_tensor* y, const void* wa, const float* ba, int wa_co_pad, int wa_ci_pad,
                  const void* wb, const float* bb, int wb_ci_pad, const void* w2, const float* b2, int w2_ci_pad,
                  int shortcut, void* stream);
+/* The same block on tcgen05 (csrc/c3k2_tc.cu): intermediates stay in shared memory, each epilogue writes the swizzled
+ * K-major tile that is the next tcgen05.mma's A operand.  Parity-tested; measured 1.5x slower than the mma.sync kernel on
+ * these thin shapes (profiles/r02_c3k2_tc.md), so yl_c3k2_tail only dispatches to it under YL_C3K2_TC=1.  c in {16, 32},
+ * c2 in {32, 64, 128}. */
+int yl_c3k2_tail_tc(const yl_tensor* t, const yl_tensor* y, const void* wa, const float* ba, int wa_co_pad, int wa_ci_pad,
+                 const void* wb, const float* bb, int wb_ci_pad, const void* w2, const float* b2, int w2_ci_pad,
+                 int shortcut, void* stream);
 
 /* ---- validator metric (the caller after the path) ------------------------------------------------- */
 /* box_iou (utils/metrics.py:51-70) + match_predictions (engine/validator.py:195-233, :410-429) for a whole batch:

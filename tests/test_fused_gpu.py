@@ -49,6 +49,7 @@ def test_c3k2_tail_fused_vs_layerwise_and_fp32(c1, c2, e, shortcut, n, h, w):
 
     m = _randomise_bn(C3k2(c1, c2, 1, False, e, 1, shortcut), 3).eval().cuda()
     assert m.c in (16, 32)
+    m.fuse_tail_max_c = 32          # the plan only fuses c = 16 by default (it is faster there); the kernel covers both
     x = torch.rand(n, c1, h, w, generator=torch.Generator().manual_seed(5)) * 2 - 1
     os.environ["YL_C3K2_FUSE"] = "1"
     m._yl_invalidate()
@@ -69,6 +70,27 @@ def test_c3k2_tail_fused_vs_layerwise_and_fp32(c1, c2, e, shortcut, n, h, w):
     assert tol(y_u - ref, ref)
     # fused and layer-by-layer round h and y2 to bf16 at the same points: they differ only by accumulation order
     assert float((y_f - y_u).abs().max()) <= 3e-2, float((y_f - y_u).abs().max())
+
+
+@pytest.mark.parametrize("c1,c2,e,shortcut,n,h,w", [
+    (32, 64, 0.25, True, 2, 24, 40), (64, 128, 0.25, True, 1, 17, 23), (64, 64, 0.5, False, 2, 16, 16),
+    (32, 32, 0.5, True, 3, 8, 16), (64, 128, 0.25, True, 2, 80, 80),
+])
+def test_c3k2_tail_tcgen05_version_vs_layerwise(c1, c2, e, shortcut, n, h, w):
+    """The tcgen05 version of the fused tail (smem-resident intermediates, epilogue -> next MMA's A operand; opt-in, see
+    profiles/r02_c3k2_tc.md) agrees with the layer-by-layer path up to accumulation order, incl. ragged tiles."""
+    from yololite.nn.modules import C3k2
+
+    m = _randomise_bn(C3k2(c1, c2, 1, False, e, 1, shortcut), 3).eval().cuda()
+    m.fuse_tail_max_c, m.tail_impl = 32, "tc"
+    x = torch.rand(n, c1, h, w, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    y_tc = m(x.cuda()).float().cpu()
+    kinds = [md["kind"] for md in next(iter(m.__dict__["_yl_plans"].values()))[0].meta]
+    assert "c3k2_tail" in kinds
+    m.fuse_tail = False
+    m._yl_invalidate()
+    y_u = m(x.cuda()).float().cpu()
+    assert float((y_tc - y_u).abs().max()) <= 3e-2, float((y_tc - y_u).abs().max())
 
 
 def test_c3k2_tail_is_used_by_the_plan():
@@ -140,4 +162,4 @@ def test_model_uses_fused_stem_and_tails():
     x = torch.rand(1, 3, 64, 64, device="cuda")
     m.infer(x)
     kinds = [md["kind"] for md in m._get_plan(x.shape, x.device)[0].meta]
-    assert kinds[0] == "stem_fused" and kinds.count("c3k2_tail") == 3, kinds[:8]
+    assert kinds[0] == "stem_fused" and kinds.count("c3k2_tail") == 1, kinds[:8]    # only the c = 16 block (layer 2)

@@ -410,6 +410,21 @@ int launch_c3k2_tc(const yl_tensor* t, const yl_tensor* y, const void* wa, const
                    cudaStream_t stream);
 }  // namespace yl
 
+// The tcgen05 version of the same block (c3k2_tc.cu), whatever YL_C3K2_TC says: A/B runs and parity tests.
+extern "C" int yl_c3k2_tail_tc(const yl_tensor* t, const yl_tensor* y, const void* wa, const float* ba, int wa_co_pad,
+                               int wa_ci_pad, const void* wb, const float* bb, int wb_ci_pad, const void* w2,
+                               const float* b2, int w2_ci_pad, int shortcut, void* stream) {
+    YL_CHECK(t && y && t->data && y->data && wa && wb && w2 && ba && bb && b2, YL_ERR_ARG, "null pointer");
+    YL_CHECK(t->dtype == YL_BF16 && y->dtype == YL_BF16, YL_ERR_ARG, "c3k2 tail tensors must be bf16");
+    YL_CHECK(t->n == y->n && t->h == y->h && t->w == y->w && t->c % 32 == 0, YL_ERR_ARG, "c3k2 tail shape mismatch");
+    YL_CHECK(t->coff % 8 == 0 && t->cstride % 8 == 0 && y->coff % 8 == 0 && y->cstride % 8 == 0, YL_ERR_ARG,
+             "c3k2 tail needs 8-channel alignment");
+    const int c = t->c / 2;
+    YL_CHECK(wa_co_pad >= c / 2 && wa_ci_pad == c && wb_ci_pad == (c / 2 + 7) / 8 * 8 && w2_ci_pad == 3 * c, YL_ERR_ARG,
+             "packed weight layouts do not match the block");
+    return yl::launch_c3k2_tc(t, y, wa, ba, wa_ci_pad, wb, bb, wb_ci_pad, w2, b2, w2_ci_pad, shortcut, (cudaStream_t)stream);
+}
+
 extern "C" int yl_c3k2_tail_supported(int c, int c2) {
     return (c == 16 || c == 32) && (c2 == 32 || c2 == 64 || c2 == 128 || c2 == 256);
 }

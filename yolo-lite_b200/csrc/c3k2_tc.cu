@@ -393,7 +393,8 @@ int launch_c3k2_tc(const yl_tensor* t, const yl_tensor* y, const void* wa, const
                    const float* bb, int wb_ci_pad, const void* w2, const float* b2, int w2_ci_pad, int shortcut,
                    cudaStream_t stream) {
     const int C = t->c / 2, C2 = y->c;
-    YL_CHECK(c3k2_tc_supported(C, C2), YL_ERR_UNSUPPORTED, "c3k2 tcgen05 tail: c = %d, c2 = %d not built", C, C2);
+    YL_CHECK((C == 16 || C == 32) && (C2 == 32 || C2 == 64 || C2 == 128), YL_ERR_UNSUPPORTED,
+             "c3k2 tcgen05 tail: c = %d, c2 = %d not built", C, C2);
     EncodeTiledFn enc = get_encode_tiled();
     YL_CHECK(enc != nullptr, YL_ERR_CUDA, "yl_init() was not called (TMA encoder unresolved)");
     C3k2TcParams p;

@@ -233,13 +233,16 @@ class Builder:
                    desc=f"[{x.c}->{pc0.co} k3s2, {pc0.co}->{pc1.co} k3s2] {x.h}x{x.w} nchw-f32 in", writes=(y,))
         return y
 
-    def c3k2_tail(self, t: View, pa: PackedConv, pb: PackedConv, p2: PackedConv, shortcut: bool, out=None) -> View:
-        """Fused [Bottleneck(3x3, 3x3) + C2f.cv2] on t = cv1(x) = [y0 | y1] (see yl_c3k2_tail)."""
+    def c3k2_tail(self, t: View, pa: PackedConv, pb: PackedConv, p2: PackedConv, shortcut: bool, out=None,
+                  impl: str = "auto") -> View:
+        """Fused [Bottleneck(3x3, 3x3) + C2f.cv2] on t = cv1(x) = [y0 | y1] (see yl_c3k2_tail); impl="tc" forces the
+        tcgen05 version (yl_c3k2_tail_tc)."""
         y = self._out(out, t.n, t.h, t.w, p2.co)
         tt, yt = t.ct(), y.ct()
         c = t.c // 2
         px = t.n * t.h * t.w
-        self._push(self.lib.yl_c3k2_tail, C.byref(tt), C.byref(yt), pa.w.data_ptr(), pa.bias.data_ptr(), pa.co_pad,
+        self._push(self.lib.yl_c3k2_tail_tc if impl == "tc" else self.lib.yl_c3k2_tail, C.byref(tt), C.byref(yt),
+                   pa.w.data_ptr(), pa.bias.data_ptr(), pa.co_pad,
                    pa.ci_pad, pb.w.data_ptr(), pb.bias.data_ptr(), pb.ci_pad, p2.w.data_ptr(), p2.bias.data_ptr(),
                    p2.ci_pad, int(bool(shortcut)), keep=(tt, yt, pa, pb, p2), kind="c3k2_tail",
                    bytes_=px * (t.c + p2.co) * 2 + (pa.w.numel() + pb.w.numel() + p2.w.numel()) * 2,

@@ -59,8 +59,14 @@ class C2f(YLModule):
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=((3, 3), (3, 3)), e=1.0) for _ in range(n))
 
-    #: run [Bottleneck + cv2] as ONE kernel when the block is thin enough (c in {16, 32}); YL_C3K2_FUSE=0 disables
+    #: run [Bottleneck + cv2] as ONE kernel when the block is thin enough; YL_C3K2_FUSE=0 disables
     fuse_tail = True
+    #: ... i.e. c <= this.  Measured after the round-2 conv_tc epilogue work (gpurun_out/ab2, yolo11n bs=64): the c = 16
+    #: block at 160x160 is 139 us fused vs 180 us layer by layer, but the c = 32 blocks at 80x80 are 96 / 79 us fused vs
+    #: 79 / 67 us layer by layer (the tcgen05 1x1 now streams at 5.7 TB/s), so only the thinnest block stays fused
+    fuse_tail_max_c = 16
+    #: "auto" = the mma.sync kernel (or whatever YL_C3K2_TC selects); "tc" = the tcgen05 version (A/B, parity tests)
+    tail_impl = "auto"
 
     def _tail_fusable(self, out):
         import os
@@ -80,6 +86,8 @@ class C2f(YLModule):
         if b.cv1.conv.kernel_size != (3, 3) or b.cv2.conv.kernel_size != (3, 3) or self.cv2.conv.kernel_size != (1, 1):
             return False
         c = self.c
+        if c > self.fuse_tail_max_c:
+            return False
         if b.cv1.conv.in_channels != c or b.cv1.conv.out_channels != c // 2 or b.cv2.conv.out_channels != c:
             return False
         return bool(_C.load().yl_c3k2_tail_supported(c, self.cv2.conv.out_channels))
@@ -90,7 +98,7 @@ class C2f(YLModule):
             t = self.cv1._emit(g, x)                 # [y0 | y1]: the only intermediate that touches HBM
             b = self.m[0]
             return g.c3k2_tail(t, packed(b.cv1.conv, b.cv1.bn, b.cv1), packed(b.cv2.conv, b.cv2.bn, b.cv2),
-                               packed(self.cv2.conv, self.cv2.bn, self.cv2), b.add, out=out)
+                               packed(self.cv2.conv, self.cv2.bn, self.cv2), b.add, out=out, impl=self.tail_impl)
         cat = g.alloc(x.n, x.h, x.w, (2 + n) * c)
         self.cv1._emit(g, x, out=cat.slice(0, 2 * c))
         prev = cat.slice(c, c)
