@@ -28,7 +28,7 @@ e1.record()
 torch.cuda.synchronize()
 lib.yl_debug_nms_phases(None)
 t = buf.cpu().numpy().astype(float)
-names = ["setup", "stage+sort", "vs kept", "compact", "pairwise", "resolve"]
+names = ["setup", "stage+sort", "vs kept + block matrix", "(unused)", "(unused)", "greedy+append"]
 tot = t[:, :6].sum(1)
 print(f"B={B}: filter+select {e0.elapsed_time(e1) * 1e3:.1f} us; per-image select cycles: mean {tot.mean():.0f} max {tot.max():.0f}"
       f" ({tot.max() / 1.965e3:.1f} us @1.965 GHz)")

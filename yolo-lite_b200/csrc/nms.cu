@@ -11,10 +11,12 @@
 //                               the result is independent of the (atomic) compaction order.
 // Kernel 2  nms_select_kernel   one CTA per image: shared-memory bitonic sort of the keys (radix-select
 //                               rounds first when there are more than SORT_CAP candidates, which also
-//                               implements the max_nms top-k), then greedy suppression in sorted order:
-//                               512 candidates at a time are tested against the kept list, survivors are
-//                               compacted, their pairwise IoU bitmask is staged in shared memory and one
-//                               warp resolves it serially; stops at max_det survivors.
+//                               implements the max_nms top-k), then greedy suppression in sorted order, 32
+//                               candidates (one per lane) at a time: all 32 warps test them against their share
+//                               of the kept list, warp 0 resolves the block's 32 x 32 suppression matrix with
+//                               register shuffles and appends the survivors; stops at max_det survivors.
+//                               Images whose classes are provably separated by the class offsets take the
+//                               class-wise path instead (select_classwise).
 // IoU arithmetic follows torchvision's CPU kernel operation by operation (no FMA contraction, same
 // std::max/std::min operand order, fp32 IoU compared against the double threshold).
 #include <math.h>
@@ -145,7 +147,6 @@ struct SelParams {
     int max_det, max_nms;
     int kept_in_smem;
     int classwise;       // allow the per-class path (A/B switch YL_NMS_CLASSWISE, default on)
-    int first_chunk;     // size of the first greedy chunk (YL_NMS_CHUNK0, default 64; kChunk = fixed 512-candidate chunks)
     long long* dbg;      // optional [B][8] phase cycle counters (tools/nms_phases.py); NULL in production
     float* kept_ws;      // global kept-list storage when max_det is large: [B][max_det][5] + keys
     unsigned long long* kept_keys_ws;
@@ -181,6 +182,36 @@ __device__ __forceinline__ bool iou_suppresses(const float4 bi, float ai, const 
         return __fdiv_rn(inter, uni) > t.thr;  // NaN / inf / non-positive union: the reference's own arithmetic
     const double lhs = (double)inter, rhs = t.mid * (double)uni;
     return t.tie_up ? (lhs >= rhs) : (lhs > rhs);
+}
+
+// The global loads of fetch_box alone (so a caller can put other work between the loads and their use) ...
+template <int MODE>
+__device__ __forceinline__ float4 fetch_raw(const SelParams& p, int b, unsigned long long key) {
+    const uint32_t idx = (uint32_t)(key & 0xffffffffull);
+    if (MODE == 0) {
+        const int a = (int)(idx / (uint32_t)p.nc);
+        const float* q = p.pred + (long long)b * (4 + p.nc) * p.A + a;
+        return make_float4(__ldg(q), __ldg(q + p.A), __ldg(q + 2 * (long long)p.A), __ldg(q + 3 * (long long)p.A));
+    }
+    return __ldg(reinterpret_cast<const float4*>(p.pred) + idx);
+}
+// ... and the arithmetic: offset box (the one NMS works on) + its area, from the raw values (cx, cy, w, h | xyxy)
+template <int MODE>
+__device__ __forceinline__ void finish_box(const SelParams& p, unsigned long long key, const float4 v, float4* off, float* area) {
+    if (MODE == 0) {
+        const uint32_t idx = (uint32_t)(key & 0xffffffffull);
+        const int a = (int)(idx / (uint32_t)p.nc);
+        const int c = (int)(idx - (uint32_t)a * (uint32_t)p.nc);
+        const float hw = v.z * 0.5f, hh = v.w * 0.5f;
+        const float o = __fmul_rn((float)c, p.max_wh);
+        off->x = __fadd_rn(__fsub_rn(v.x, hw), o);
+        off->y = __fadd_rn(__fsub_rn(v.y, hh), o);
+        off->z = __fadd_rn(__fadd_rn(v.x, hw), o);
+        off->w = __fadd_rn(__fadd_rn(v.y, hh), o);
+    } else {
+        *off = v;
+    }
+    *area = __fmul_rn(__fsub_rn(off->z, off->x), __fsub_rn(off->w, off->y));
 }
 
 template <int MODE>
@@ -495,7 +526,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
         __syncthreads();
     }
 
-    int chunk = p.first_chunk;   // candidates per greedy chunk (grows up to kChunk)
+    if (tid == 0) misc[5] = 0;   // lanes of the current 32-candidate block suppressed by the kept list
+    __syncthreads();
     long long tph = clock64(), acc_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define YL_PH(k)                                   \
     do {                                           \
@@ -639,123 +671,88 @@ __global__ void __launch_bounds__(kSelThreads, 1) nms_select_kernel(const SelPar
         }
 
         YL_PH(1);   // round staging: gather + sort
-        // ---------------- greedy suppression over skeys[0..m) in chunks
+        // ---------------- greedy suppression over skeys[0..m), 32 candidates (one per lane) at a time, in score order
+        // Before the block barrier every warp (i) tests the block's candidates against ITS share of the kept list (kept
+        // boxes warp, warp + 32, ...) and ORs the suppressed lanes into one shared word, (ii) computes row `warp` of the
+        // block's 32 x 32 suppression matrix (candidate `warp` against the later candidates, one IoU per lane) and
+        // (iii) issues the global loads of the NEXT block's boxes.  After it warp 0 runs the greedy pass over the matrix
+        // rows of the surviving candidates and appends the kept ones.  No speculative pairwise work beyond 32 x 32,
+        // two block barriers per 32 candidates, the scan stops at max_det kept boxes.
         const IouThr thr = {p.thr, p.thr_mid, p.thr_tie_up};
-        // Chunks grow 64 -> 128 -> 256 -> 512: the pairwise test among a chunk's survivors is speculative work (most of a
-        // dense blob is suppressed by the first few kept boxes), so the first chunks are kept small; once there are kept
-        // boxes, step 1 prunes a chunk before the quadratic step sees it.
-        for (int s0 = 0, cnt = 0; s0 < m && nk < p.max_det; s0 += cnt) {
-            cnt = (m - s0) < chunk ? (m - s0) : chunk;
-            if (chunk < kChunk) chunk <<= 1;
-            // 1. candidate vs kept list: two threads per candidate, each scanning every other kept box
-            const int ci = tid >> 1, half = tid & 1;
-            float4 ob = make_float4(0, 0, 0, 0), rb;
-            float ar = 0.f, sc;
-            int cl;
-            bool alive = false;
-            if (ci < cnt) {
-                fetch_box<MODE>(p, b, skeys[s0 + ci], &rb, &ob, &ar, &sc, &cl);
-                alive = true;
-                for (int i = half; i < nk; i += 2) {
-                    const float4 kb = make_float4(kept[i * 5 + 0], kept[i * 5 + 1], kept[i * 5 + 2], kept[i * 5 + 3]);
-                    if (iou_suppresses(kb, kept[i * 5 + 4], ob, ar, thr)) {
-                        alive = false;
-                        break;
-                    }
-                }
+        bool valid = lane < m;
+        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f), rb;
+        float ar = 0.f, sc;
+        int cl;
+        unsigned long long key = 0;
+        if (valid) {
+            key = skeys[lane];
+            fetch_box<MODE>(p, b, key, &rb, &ob, &ar, &sc, &cl);
+        }
+        for (int s0 = 0; s0 < m && nk < p.max_det; s0 += 32) {
+            // (iii) next block's candidates: only the loads are issued here, they fly under (i) and (ii)
+            const bool nvalid = s0 + 32 + lane < m;
+            float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned long long nkey = 0;
+            if (nvalid) {
+                nkey = skeys[s0 + 32 + lane];
+                nraw = fetch_raw<MODE>(p, b, nkey);
             }
-            // (the shuffle must be executed by every lane: no short-circuit in front of it)
-            const int other_alive = __shfl_xor_sync(0xffffffffu, (int)alive, 1);
-            alive = alive && other_alive && (half == 0);  // the even thread of the pair carries the candidate on
-            YL_PH(2);   // candidates vs kept
-            // 2. ordered compaction of survivors
-            const unsigned bal = __ballot_sync(0xffffffffu, alive);
-            if (lane == 0) misc[8 + warp] = __popc(bal);
+            // (i)
+            bool dead = false;
+            for (int i = warp; i < nk; i += kSelThreads / 32) {
+                const float4 kb = make_float4(kept[i * 5 + 0], kept[i * 5 + 1], kept[i * 5 + 2], kept[i * 5 + 3]);
+                if (valid && !dead && iou_suppresses(kb, kept[i * 5 + 4], ob, ar, thr)) dead = true;
+            }
+            const unsigned dbits = __ballot_sync(0xffffffffu, dead);
+            if (lane == 0 && dbits) atomicOr(reinterpret_cast<unsigned*>(&misc[5]), dbits);
+            // (ii) row `warp`
+            {
+                float4 bi;
+                bi.x = __shfl_sync(0xffffffffu, ob.x, warp);
+                bi.y = __shfl_sync(0xffffffffu, ob.y, warp);
+                bi.z = __shfl_sync(0xffffffffu, ob.z, warp);
+                bi.w = __shfl_sync(0xffffffffu, ob.w, warp);
+                const float ai = __shfl_sync(0xffffffffu, ar, warp);
+                const bool sup = valid && lane > warp && (s0 + warp < m) && iou_suppresses(bi, ai, ob, ar, thr);
+                const unsigned bits = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) misc[8 + warp] = (int)bits;
+            }
             __syncthreads();
+            YL_PH(2);   // vs kept + block matrix row
             if (warp == 0) {
-                int v = misc[8 + lane];
-                int incl = v;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
+                const uint32_t alive_mask = __ballot_sync(0xffffffffu, valid) & ~(uint32_t)misc[5];
+                const uint32_t rowbits = (uint32_t)misc[8 + lane];
+                uint32_t live = alive_mask, keep = 0;
+                int room = p.max_det - nk;
+                while (live && room > 0) {
+                    const int l = __ffs(live) - 1;
+                    keep |= 1u << l;
+                    --room;
+                    live &= ~(__shfl_sync(0xffffffffu, rowbits, l) | (1u << l));
                 }
-                misc[8 + lane] = incl - v;  // exclusive
-                if (lane == 31) misc[3] = incl;
-            }
-            __syncthreads();
-            const int L = misc[3];
-            if (alive) {
-                const int pos = misc[8 + warp] + __popc(bal & ((1u << lane) - 1u));
-                cbox[pos] = ob;
-                carea[pos] = ar;
-                csrc[pos] = s0 + ci;
-            }
-            __syncthreads();
-            YL_PH(3);   // compaction
-            // 3. pairwise bitmask among survivors: only the words on or right of the diagonal exist.  A warp owns
-            //    rows warp, warp+32, ... (every 32-row block gives each warp one row, so the triangle is balanced);
-            //    its lanes take the 32 columns of one word: box j is read conflict-free, box i is a broadcast.
-            const int W = (L + 31) >> 5;
-            for (int i = warp; i < L; i += kSelThreads / 32) {
-                const float4 bi = cbox[i];
-                const float ai = carea[i];
-                for (int wd = i >> 5; wd < W; ++wd) {
-                    const int j = (wd << 5) + lane;
-                    const bool sup = (j > i) && (j < L) && iou_suppresses(bi, ai, cbox[j], carea[j], thr);
-                    const uint32_t bits = __ballot_sync(0xffffffffu, sup);
-                    if (lane == 0) mask[i * kMaskWords + wd] = bits;
+                if ((keep >> lane) & 1u) {
+                    const int pos = nk + __popc(keep & ((1u << lane) - 1u));
+                    kept[pos * 5 + 0] = ob.x;
+                    kept[pos * 5 + 1] = ob.y;
+                    kept[pos * 5 + 2] = ob.z;
+                    kept[pos * 5 + 3] = ob.w;
+                    kept[pos * 5 + 4] = ar;
+                    kept_keys[pos] = key;
                 }
-            }
-            __syncthreads();
-            YL_PH(4);   // pairwise mask
-            // 4. resolve by warp 0, one block of 32 candidates at a time: the 32 x 32 diagonal block is resolved
-            //    with register shuffles only (lane l holds row l's diagonal word), then the kept rows are OR-ed into
-            //    the removed set (lane w owns word w) and appended to the kept list in parallel.
-            if (warp == 0) {
-                uint32_t rem = 0;
-                int nk_l = nk;
-                for (int blk = 0; blk < W && nk_l < p.max_det; ++blk) {
-                    const int r = blk * 32 + lane;
-                    const uint32_t diag = (r < L) ? mask[r * kMaskWords + blk] : 0u;
-                    const int nrows = L - blk * 32;
-                    const uint32_t vm = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
-                    uint32_t live = ~__shfl_sync(0xffffffffu, rem, blk) & vm;
-                    uint32_t keepbits = 0;
-                    int room = p.max_det - nk_l;
-                    while (live && room > 0) {
-                        const int l = __ffs(live) - 1;
-                        keepbits |= 1u << l;
-                        --room;
-                        live &= ~(__shfl_sync(0xffffffffu, diag, l) | (1u << l));
-                    }
-                    // removed set of the later blocks
-                    if (lane > blk && lane < W) {
-                        uint32_t kb = keepbits;
-                        while (kb) {
-                            const int l = __ffs(kb) - 1;
-                            kb &= kb - 1;
-                            rem |= mask[(blk * 32 + l) * kMaskWords + lane];
-                        }
-                    }
-                    if ((keepbits >> lane) & 1u) {
-                        const int pos = nk_l + __popc(keepbits & ((1u << lane) - 1u));
-                        const float4 bb = cbox[r];
-                        kept[pos * 5 + 0] = bb.x;
-                        kept[pos * 5 + 1] = bb.y;
-                        kept[pos * 5 + 2] = bb.z;
-                        kept[pos * 5 + 3] = bb.w;
-                        kept[pos * 5 + 4] = carea[r];
-                        kept_keys[pos] = skeys[csrc[r]];
-                    }
-                    nk_l += __popc(keepbits);
+                if (lane == 0) {
+                    misc[4] = nk + __popc(keep);
+                    misc[5] = 0;
                 }
-                if (lane == 0) misc[4] = nk_l;
+                YL_PH(5);   // greedy pass + append
             }
             __threadfence_block();
             __syncthreads();
             nk = misc[4];
-            __syncthreads();
-            YL_PH(5);   // serial resolve
+            valid = nvalid;
+            key = nkey;
+            ob = make_float4(0.f, 0.f, 0.f, 0.f);
+            ar = 0.f;
+            if (valid) finish_box<MODE>(p, key, nraw, &ob, &ar);
         }
         processed += consumed;
     }
@@ -796,17 +793,12 @@ static size_t sel_smem_bytes(int max_det, bool kept_in_smem) {
 
 static int g_sel_max_smem = 0;
 static int g_nms_classwise = 1;   // YL_NMS_CLASSWISE, read once in yl_init
-static int g_nms_chunk0 = 64;     // YL_NMS_CHUNK0
 static thread_local long long* g_nms_dbg = nullptr;   // yl_debug_nms_phases
 
 int init_nms() {
     {
         const char* e = getenv("YL_NMS_CLASSWISE");
         g_nms_classwise = (e && *e) ? (atoi(e) != 0) : 1;
-        const char* c0 = getenv("YL_NMS_CHUNK0");
-        int v = (c0 && *c0) ? atoi(c0) : 64;
-        g_nms_chunk0 = 32;
-        while (g_nms_chunk0 < v && g_nms_chunk0 < kChunk) g_nms_chunk0 <<= 1;
     }
     int dev = 0;
     YL_CUDA(cudaGetDevice(&dev));
@@ -883,7 +875,6 @@ static int launch_select(const float* pred, int B, int nc, int A, size_t cap, co
     p.max_nms = max_nms;
     p.kept_in_smem = 1;
     p.classwise = g_nms_classwise;
-    p.first_chunk = yl::g_nms_chunk0;
     p.dbg = yl::g_nms_dbg;
     p.kept_ws = nullptr;
     p.kept_keys_ws = nullptr;
@@ -1016,7 +1007,6 @@ int yl_nms_boxes(const float* boxes, const float* scores, int n, double iou_thre
     p.max_nms = n;
     p.kept_in_smem = 0;
     p.classwise = 0;
-    p.first_chunk = yl::g_nms_chunk0;
     p.dbg = yl::g_nms_dbg;
     p.kept_ws = kept_ws;
     p.kept_keys_ws = kept_keys_ws;
