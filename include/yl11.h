@@ -156,6 +156,31 @@ typedef struct yl_conv_tc_plan {
 } yl_conv_tc_plan;
 int yl_conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out);
 
+/* A chain of convolution layers in ONE launch (csrc/conv_chain.cu): the consecutive Conv modules of the small feature
+ * maps — the C3k / Bottleneck chains, SPPF and C2PSA 1x1 convs of nn/tasks.py:118-145's layer loop (block.py:165-184,
+ * 330-343, 720-739, 999-1038) — each of which is a launch-latency chain rather than work when run as its own kernel.
+ * One thread-block cluster (4 CTAs) owns one image for the whole chain; layers hand over through L2 and a cluster
+ * barrier.  Every layer is a yl_conv_args of the bf16 -> bf16 kind (k in {1,3}, stride in {1,2}, optional SiLU /
+ * residual / 2x-upsampled second destination; no Detect epilogue), all with the same batch; a layer may read anything
+ * earlier layers of the chain (or earlier launches) wrote.  Results are bit-identical to the layers launched one by one.
+ *   yl_conv_chain_build plans the layers and fills `desc_dev` (device, >= yl_conv_chain_desc_bytes(n), 128-byte aligned,
+ *   owned by the caller, must outlive the chain); it synchronises `stream` once.  yl_conv_chain_run is asynchronous and
+ *   graph-capturable like every other launch. */
+typedef struct yl_conv_chain {
+    void* desc;
+    int32_t n_layers, batch, cluster, smem_bytes, tmem_cols, reserved;
+} yl_conv_chain;
+size_t yl_conv_chain_desc_bytes(int n_layers);
+/* 1 if this layer can be a member of a chain */
+int yl_conv_chain_supported(const yl_conv_args* a);
+int yl_conv_chain_build(const yl_conv_args* layers, int n_layers, void* desc_dev, size_t desc_bytes, yl_conv_chain* out,
+                        void* stream);
+int yl_conv_chain_run(const yl_conv_chain* chain, void* stream);
+/* Debug aid (tools/chain_timeline.py): chain launches of the calling thread record, per layer, 6 %globaltimer stamps (ns)
+ * of CTA 0 into device_buf[layer][8]: layer start, first operands landed, last MMA issued, epilogue entered, epilogue
+ * returned (stores complete), cluster barrier passed.  NULL disables. */
+int yl_conv_chain_debug(unsigned long long* device_buf);
+
 /* First layer fused with the image ingest (predictor.py:81-84 + conv.py:35-53): reads the NCHW fp32 batch
  * (values rounded to bf16 like every other activation), 3x3 stride-2 pad-1 conv, <= 4 input channels, folded
  * BN + SiLU, NHWC bf16 out.  y->c in {16, 32, 48, 64, 96}. */

@@ -163,3 +163,97 @@ def test_model_uses_fused_stem_and_tails():
     m.infer(x)
     kinds = [md["kind"] for md in m._get_plan(x.shape, x.device)[0].meta]
     assert kinds[0] == "stem_fused" and kinds.count("c3k2_tail") == 1, kinds[:8]    # only the c = 16 block (layer 2)
+
+
+# ------------------------------------------------------------------------------------------------ conv chains
+def _chain_fixture(n, hw, seed):
+    """A small net of plain convs that exercises every member kind of a chain: 1x1, 3x3, stride 2, residual, channel
+    slices (concat by aliasing), no activation, and a result stored twice (conv resolution + 2x upsampled)."""
+    from yololite import _ops
+
+    g = torch.Generator().manual_seed(seed)
+
+    def pc(ci, co, k):
+        w = torch.randn(co, ci, k, k, generator=g) * (1.5 / (ci * k * k) ** 0.5)
+        return _ops.pack_conv(w, bn=None, conv_bias=torch.randn(co, generator=g) * 0.1)
+
+    x = torch.randn(n, hw, hw, 64, generator=g).to(torch.bfloat16).cuda()
+    packs = {"a": pc(64, 128, 1), "b": pc(64, 64, 3), "c": pc(64, 64, 3), "d": pc(192, 256, 1), "e": pc(256, 128, 3),
+             "f": pc(128, 96, 1), "g": pc(96, 32, 3), "h": pc(32, 64, 1)}
+    return x, packs
+
+
+def _emit_chain_net(g, x, packs):
+    from yololite._ops import View
+    from yololite._plan import DualDest
+
+    xv = View(x, 0, 64)
+    cat = g.alloc(xv.n, xv.h, xv.w, 192)                               # [a (128) | c (64)]
+    a = g.conv(xv, packs["a"], 1, True, out=cat.slice(0, 128))
+    b = g.conv(a.slice(64, 64), packs["b"], 1, True)
+    g.conv(b, packs["c"], 1, True, out=cat.slice(128, 64), res=cat.slice(64, 64))     # residual = upper half of a
+    d = g.conv(cat, packs["d"], 1, True)
+    e = g.conv(d, packs["e"], 2, True)                                 # stride 2: hw -> hw / 2
+    dual = DualDest(None, None)
+    f = g.conv(e, packs["f"], 1, False, out=dual)                      # no activation, stored at hw/2 and at hw
+    gg = g.conv(f, packs["g"], 1, True)
+    h = g.conv(gg, packs["h"], 1, True, res=None)
+    return [cat, d, e, f, dual.up_view, gg, h]
+
+
+@pytest.mark.parametrize("n,hw", [(3, 20), (2, 40), (1, 24), (5, 10)])
+def test_conv_chain_is_bit_identical_to_its_layers(n, hw):
+    """yl_conv_chain (one cluster per image walks all layers) against the same layers launched one by one: every
+    intermediate and final tensor bit for bit, incl. ragged tiles (24 = 128-pixel tiles do not divide the map) and maps
+    smaller than one tile (10x10 -> 5x5)."""
+    from yololite import _plan
+
+    dev = torch.device("cuda", 0)
+    x, packs = _chain_fixture(n, hw, 100 + hw)
+    outs = {}
+    for mode in ("layers", "chain"):
+        g = _plan.Builder(dev)
+        g.chain_enabled = mode == "chain"
+        g.chain_min_batch = 1
+        views = _emit_chain_net(g, x, packs)
+        plan = g.finish()
+        kinds = [md["kind"] for md in plan.meta]
+        if mode == "chain":
+            assert kinds == ["conv_chain"], kinds
+            assert len(plan.meta[0]["members"]) == 8
+        else:
+            assert kinds == ["conv_tc"] * 8, kinds
+        plan.run_eager()
+        plan.run_eager()            # idempotent: a second pass over the same buffers gives the same result
+        torch.cuda.synchronize()
+        outs[mode] = [v.torch_nhwc().clone() for v in views]
+    for i, (a, b) in enumerate(zip(outs["layers"], outs["chain"])):
+        assert a.shape == b.shape
+        assert torch.equal(a, b), f"tensor {i}: max diff {float((a.float() - b.float()).abs().max())}"
+    assert float(outs["chain"][-1].float().abs().max()) > 0
+
+
+def test_model_with_chains_equals_model_without(monkeypatch):
+    """yolo11n at 640x640: the plan with conv chains (forced on at this small batch) gives the same prediction, bit for
+    bit, as the layer-by-layer plan; and the chains swallow the 20x20 / 40x40 convolutions (<= 12 launches remain on
+    those maps)."""
+    from bench import randomise_model_
+    from yololite.nn.tasks import DetectionModel
+
+    x = torch.rand(3, 3, 640, 640, generator=torch.Generator().manual_seed(9)).cuda()
+    ys, metas = {}, {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("YL_CHAIN", mode)
+        monkeypatch.setenv("YL_CHAIN_MIN_BATCH", "1")
+        torch.manual_seed(4)            # same conv weights in both builds
+        m = randomise_model_(DetectionModel("yolo11n.yaml", verbose=False)).eval().cuda()
+        y, _ = m.infer(x)
+        torch.cuda.synchronize()
+        ys[mode] = y.clone()
+        metas[mode] = m._get_plan(x.shape, x.device)[0].meta
+    assert torch.equal(ys["0"], ys["1"]), float((ys["0"] - ys["1"]).abs().max())
+    chains = [md for md in metas["1"] if md["kind"] == "conv_chain"]
+    assert chains and sum(len(c["members"]) for c in chains) >= 40, [len(c["members"]) for c in chains]
+    assert not [md for md in metas["0"] if md["kind"] == "conv_chain"]
+    small = [md for md in metas["1"] if md["kind"] == "conv_tc" and ("20x20" in md["desc"] or "40x40" in md["desc"])]
+    assert len(small) <= 8, [md["desc"] for md in small]      # what remains: the Detect head's last 1x1 convs

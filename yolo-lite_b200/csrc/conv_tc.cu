@@ -27,385 +27,10 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace yl {
 
-struct ConvTcParams {
-    CUtensorMap tmA[4];
-    CUtensorMap tmB;
-    CUtensorMap tmY[5];          // [0] plain destination, [1..4] parity planes of the 2x-upsampled destination
-    int y_map_first, y_map_last; // stores go to tmY[first..last)
-    int Ho, Wo, Nimg;            // conv output dims per image, images (flat mode: 1, total pixels, 1)
-    int tiles_w, tiles_h, tiles_n;
-    int TW, TH, TN;              // A-tile box: TW*TH*TN <= 128 rows (pixels), may span images
-    int m_tiles, n_tiles, total_tiles;
-    FastDiv fd_ntiles, fd_tiles_w, fd_tiles_h;   // tile index -> (n tile, w tile, h tile, image tile)
-    int ksize, stride, pad;
-    int ci_pad;                  // K elements per tap in the packed weights
-    int kblk, cin_blocks;        // channels per k-iteration, iterations per tap
-    int co_tile;                 // UMMA N
-    int acc_stride;              // TMEM columns per accumulator stage (co_tile rounded up to the chunk width)
-    int stages;
-    // halo-patch mode (3x3 stride 1, thin channels): ONE TMA box {kblk, patch_pw, TH+2} per tile holds every
-    // tap's A operand (taps are shifted windows of it); the 9-tap weights stay resident in smem
-    int patch, patch_pw, patch_bo;
-    CUtensorMap tmW3;            // weights as {ci, co, tap}: box {kblk, co_tile, 9} -> smem [tap][co_tile][kblk]
-    uint32_t w_bytes;
-    // resident-weights mode (non-patch, one N tile, small K): all k-iterations' weight tiles are fetched once per
-    // CTA into smem [kiter][co_tile][kblk]; the ring then carries activations only (TMA issue rate, not bytes, is
-    // what bounds the thin layers: ~3.3 clk per box row per SM, tools/tma_bench.cu)
-    int wres;
-    int wearly;                  // issue the resident-weight loads before the PDL dependency wait
-    uint32_t tmem_cols;
-    uint32_t a_bytes, b_bytes;   // per-stage smem footprint (1024-aligned)
-    uint32_t b_region;           // smem bytes of the weight area: ring (stages * b_bytes) or resident block
-    uint32_t tx_bytes;           // bytes one stage's two TMA boxes deliver
-    // epilogue
-    int cw;                      // accumulator columns per TMEM load (16 or 32)
-    int nchunks;
-    int stg_sub;                 // TMEM chunks per TMA store (1 or 2): a store moves stg_sub * cw channels
-    int nstore;                  // TMA stores per tile = ceil(nchunks / stg_sub)
-    int stg_bufs;                // staging tiles per epilogue group (2 = the store of chunk k overlaps chunk k+1)
-    int stg_row_bytes;           // stg_sub * cw * element size: 32, 64 or 128 (= the staging swizzle span)
-    uint32_t stg_bytes;          // per staging tile
-    int y_f32;
-    const float* bias;
-    int n_bias;                  // valid bias entries (co_pad)
-    int act;
-    int epi_kind;                // which epilogue instantiation runs (see conv_tc_kernel)
-    const __nv_bfloat16* res;
-    long long res_cstride;
-    int res_coff, res_c;
-    // fused Detect decode (flat 1x1 head convs): see yl_det_epilogue
-    int store_y;                 // 0: no NHWC destination (decode only)
-    int det_mode;                // yl_det_mode
-    float* det_pred;
-    int det_nc, det_A, det_anchor0, det_hw, det_w;
-    float det_stride;
-    long long det_M;             // valid pixels (rows beyond it belong to the ragged last tile)
-    float det_conf;              // YL_DET_CLS_FILTER: confidence threshold (strict >)
-    uint32_t* det_cand_counts;   //   per-image candidate counters of the NMS workspace
-    unsigned long long* det_cand_keys;  // per-image key lists, `det_A` entries each
-    unsigned long long* dbg;     // optional timeline slot (8 x %globaltimer ns, written by CTA 0): yl_debug_timeline
-};
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// (compiled out of the production instantiation: DBG is a template parameter of the kernel)
-#define YL_STAMP(slot)                                                          \
-    do {                                                                        \
-        if constexpr (DBG) {                                                    \
-            if (p.dbg && blockIdx.x == 0) p.dbg[slot] = globaltimer_ns();       \
-        }                                                                       \
-    } while (0)
-
-constexpr int kConvTcThreads = 320;
-constexpr int kEpiGroupThreads = 128;
-
-template <int CW>
-__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[CW]);
-template <>
-__device__ __forceinline__ void tmem_ld_cw<16>(uint32_t taddr, uint32_t (&r)[16]) {
-    tmem_ld16(taddr, r);
-}
-template <>
-__device__ __forceinline__ void tmem_ld_cw<32>(uint32_t taddr, uint32_t (&r)[32]) {
-    tmem_ld32(taddr, r);
-}
-
-// Fused Detect decode of one accumulator chunk (CW columns, bias already added) of pixel `m` (flat index over
-// (image, h, w)): box mode turns each 16-bin group into its DFL expectation and, once the four sides are
-// known, writes (cx, cy, w, h) * stride; class mode writes sigmoid(logit).  Consecutive lanes hold consecutive
-// pixels = consecutive anchors, so every channel row of the (B, 4+nc, A) prediction gets 128-byte coalesced
-// stores (head.py:95-126, block.py:51-69, tal.py:326-350).
-// YL_DET_CLS_FILTER: running best class of this thread's pixel over the accumulator chunks; after the last chunk every
-// passing anchor (best > conf, strict; ties keep the lowest class: utils/ops.py:203, 242-244) is appended to its
-// image's candidate list with the same key the NMS filter kernel would build from the stored score.  Lanes are
-// grouped by image (a 128-pixel tile may straddle two images) and each group does ONE atomicAdd.
-template <int CW>
-__device__ __forceinline__ void det_filter_chunk(const ConvTcParams& p, const float (&v)[CW], int c, long long m, int lane,
-                                                 float& best, int& bestc) {
-    if (c == 0) {
-        best = -INFINITY;
-        bestc = 0;
-    }
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-        const int ch = c * CW + i;
-        if (ch < p.det_nc) {
-            const float sc = __fdividef(1.f, 1.f + __expf(-v[i]));   // the value YL_DET_CLS would have stored
-            if (sc > best) {
-                best = sc;
-                bestc = ch;
-            }
-        }
-    }
-    if (c != p.nchunks - 1) return;
-    const bool emit = (m < p.det_M) && (best > p.det_conf);
-    if (__ballot_sync(0xffffffffu, emit) == 0u) return;
-    const int b = emit ? (int)(m / p.det_hw) : -1;
-    const unsigned grp = __match_any_sync(0xffffffffu, b);
-    if (emit) {
-        const int leader = __ffs(grp) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(p.det_cand_counts + b, (uint32_t)__popc(grp));
-        base = __shfl_sync(grp, base, leader);
-        const uint32_t pos = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-        const int al = (int)(m - (long long)b * p.det_hw);
-        const uint32_t idx = (uint32_t)(p.det_anchor0 + al) * (uint32_t)p.det_nc + (uint32_t)bestc;
-        p.det_cand_keys[(unsigned long long)b * (unsigned long long)p.det_A + pos] =
-            ((unsigned long long)score_to_desc(best) << 32) | idx;
-    }
-}
-
-template <int CW>
-__device__ __forceinline__ void det_decode_chunk(const ConvTcParams& p, const float (&v)[CW], int c, long long m,
-                                                 float (&dist)[4], int det_mode) {
-    if (m >= p.det_M) return;
-    const int b = (int)(m / p.det_hw);
-    const int al = (int)(m - (long long)b * p.det_hw);
-    float* out = p.det_pred + (long long)b * (4 + p.det_nc) * p.det_A + p.det_anchor0 + al;
-    if (det_mode == YL_DET_BOX) {
-        if (CW == 32) {  // reg_max == 16: two sides per chunk
-            float d2[2];
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-                float mx = v[sd * 16];
-#pragma unroll
-                for (int k = 1; k < 16; ++k) mx = fmaxf(mx, v[sd * 16 + k]);
-                float ssum = 0.f, e = 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float w = __expf(v[sd * 16 + k] - mx);
-                    ssum += w;
-                    e = fmaf(w, (float)k, e);
-                }
-                d2[sd] = __fdividef(e, ssum);
-            }
-            if (c == 0) {
-                dist[0] = d2[0];
-                dist[1] = d2[1];
-            } else {
-                dist[2] = d2[0];
-                dist[3] = d2[1];
-                const float ax = (float)(al % p.det_w) + 0.5f, ay = (float)(al / p.det_w) + 0.5f;
-                const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
-                out[0] = (x1 + x2) * 0.5f * p.det_stride;
-                out[(long long)p.det_A] = (y1 + y2) * 0.5f * p.det_stride;
-                out[2ll * p.det_A] = (x2 - x1) * p.det_stride;
-                out[3ll * p.det_A] = (y2 - y1) * p.det_stride;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) {
-            const int ch = c * CW + i;
-            if (ch < p.det_nc) out[(long long)(4 + ch) * p.det_A] = __fdividef(1.f, 1.f + __expf(-v[i]));
-        }
-    }
-}
-
-// One epilogue group (4 warps, thread = accumulator row) draining the tiles of its accumulator stage.
-// A "store chunk" is stg_sub TMEM chunks (<= 128 B per pixel row) staged in one swizzled tile and written by
-// one TMA store.  With two staging tiles the store of chunk k is issued after the barrier of chunk k+1, so the
-// group never waits for a TMA store to drain its source: one named barrier per store chunk, and the smem read
-// of store k overlaps the TMEM load + math of chunk k+1.
-//
-// GENERIC == false is the hot instantiation (bf16 destination, no Detect epilogue; activation / residual are compile-time
-// ACT / RES): ncu showed ~300 warp instructions per 32-column chunk of which only ~160 were the math, the rest runtime
-// flag tests, parameter reloads, swizzle arithmetic and the (disabled) timeline stamps.  GENERIC == true keeps every
-// runtime option (fp32 destination, Detect decode / class filter, no NHWC store).
-// DET (non-generic): 0 = plain bf16 NHWC store; YL_DET_BOX / YL_DET_CLS / YL_DET_CLS_FILTER = the engine path's head
-// convs, whose result feeds the fused Detect epilogue only (no NHWC store at all).
-template <int CW, bool ACT, bool RES, int DET, bool GENERIC, bool DBG>
-__device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, int g, int q, int lane, int gtid,
-                                                 uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                 uint8_t* stg, const float* sbias) {
-    const bool k_act = GENERIC ? (p.act != 0) : ACT;
-    const bool k_res = GENERIC ? (p.res != nullptr) : RES;
-    const bool k_f32 = GENERIC ? (p.y_f32 != 0) : false;
-    const int k_det = GENERIC ? p.det_mode : DET;
-    const bool k_store = GENERIC ? (p.store_y != 0) : (DET == 0);
-    const float bscale = k_act ? 0.5f : 1.0f;   // see the bias staging in the kernel prologue
-    const int row = q * 32 + lane;
-    const int tw = row % p.TW;
-    const int th = (row / p.TW) % p.TH;
-    const int tn = row / (p.TW * p.TH);
-    const uint32_t swz_mask = (uint32_t)(p.stg_row_bytes / 16 - 1);  // 1, 3 or 7 sixteen-byte chunks
-    const uint32_t row_off = (uint32_t)row * (uint32_t)p.stg_row_bytes;
-    // a row's bytes never cross a 128-byte line (row pitch 32 / 64 / 128), so the swizzle XOR is a per-thread constant
-    const uint32_t swz_xor = ((row_off >> 7) & swz_mask) << 4;
-    const uint32_t stg_base = smem_u32(stg);
-    const uint32_t sub_bytes = (uint32_t)CW * (k_f32 ? 4u : 2u);
-    const int nchunks = p.nchunks, stg_sub = p.stg_sub, nstore = p.nstore;
-    const bool dbl = p.stg_bufs == 2;
-    // the first warp of the group owns the TMA stores; one elected lane issues / commits / waits on them
-    const bool leader = (gtid < 32) && elect_one();
-    uint32_t kstore = 0;                       // running store-chunk counter (selects the staging tile)
-    int pend = 0, pc0 = 0, pw0 = 0, ph0 = 0, pi0 = 0;  // filled tile whose TMA store is not issued yet
-    uint32_t pbuf = 0;
-    float det_dist[4] = {0.f, 0.f, 0.f, 0.f};  // decode mode: DFL distances (l, t, r, b) of this thread's pixel
-    float det_best = -INFINITY;                // class-filter mode: best score / class of this thread's pixel
-    int det_bestc = 0;
-
-    int lt = g;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, lt += 2) {
-        int nt, wt, ht;
-        int mt = fast_divmod(tile, p.fd_ntiles, &nt);
-        mt = fast_divmod(mt, p.fd_tiles_w, &wt);
-        const int it = fast_divmod(mt, p.fd_tiles_h, &ht);
-        const int w0 = wt * p.TW, h0 = ht * p.TH, i0 = it * p.TN;
-        const int n0 = nt * p.co_tile;
-
-        const __nv_bfloat16* resrow = nullptr;
-        if (k_res) {
-            const int w = w0 + tw, h = h0 + th, n = i0 + tn;
-            if ((tn < p.TN) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo))
-                resrow = p.res + (((long long)n * p.Ho + h) * p.Wo + w) * p.res_cstride + p.res_coff;
-        }
-
-        const uint32_t ph = (uint32_t)(lt >> 1) & 1u;
-        mbar_wait(&tfull_bar[g], ph);
-        tc_fence_after();
-        if (leader && g == 0 && lt == 0) YL_STAMP(4);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.acc_stride);
-
-        for (int s = 0; s < nstore; ++s, ++kstore) {
-            const uint32_t buf = dbl ? (kstore & 1u) * p.stg_bytes : 0u;
-            for (int u = 0; u < stg_sub; ++u) {
-                const int c = s * stg_sub + u;
-                if (c >= nchunks) break;
-                const int col0 = n0 + c * CW;  // first output channel of this chunk
-                uint32_t acc[CW];
-                tmem_ld_cw<CW>(taddr + (uint32_t)(c * CW), acc);
-                // residual rows are independent of the accumulator: issue the loads under the TMEM latency
-                uint4 rv[CW / 8];
-                if (k_res) {
-#pragma unroll
-                    for (int i = 0; i < CW / 8; ++i) {
-                        rv[i] = make_uint4(0u, 0u, 0u, 0u);
-                        if (resrow && col0 + i * 8 < p.res_c)
-                            rv[i] = __ldg(reinterpret_cast<const uint4*>(resrow + col0) + i);
-                    }
-                }
-                tmem_ld_wait();
-                if (leader && g == 0 && lt == 0 && c < 3) YL_STAMP(c == 0 ? 8 : (c == 1 ? 12 : 14));
-                if (c == nchunks - 1) {
-                    // every TMEM read of this tile has completed: hand the accumulator back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[g]);
-                }
-                // SiLU(x) = h + h * tanh(h) with h = x / 2 (one MUFU op).  For activated convs the staged bias is b / 2 and
-                // the accumulator is scaled by 1/2 in the same FMA: h = fma(acc, 0.5, b / 2) is bit-identical to
-                // 0.5 * (acc + b) (a scaling by two commutes with the rounding) and saves an instruction per element.
-                float v[CW];
-#pragma unroll
-                for (int i = 0; i < CW; i += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + i);
-                    v[i + 0] = fmaf(__uint_as_float(acc[i + 0]), bscale, b.x);
-                    v[i + 1] = fmaf(__uint_as_float(acc[i + 1]), bscale, b.y);
-                    v[i + 2] = fmaf(__uint_as_float(acc[i + 2]), bscale, b.z);
-                    v[i + 3] = fmaf(__uint_as_float(acc[i + 3]), bscale, b.w);
-                }
-                if (k_act) {
-#pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = fmaf(v[i], tanh_approx(v[i]), v[i]);
-                }
-                if (k_res) {
-#pragma unroll
-                    for (int i = 0; i < CW / 8; ++i) {
-                        v[i * 8 + 0] += bf16lo_f(rv[i].x); v[i * 8 + 1] += bf16hi_f(rv[i].x);
-                        v[i * 8 + 2] += bf16lo_f(rv[i].y); v[i * 8 + 3] += bf16hi_f(rv[i].y);
-                        v[i * 8 + 4] += bf16lo_f(rv[i].z); v[i * 8 + 5] += bf16hi_f(rv[i].z);
-                        v[i * 8 + 6] += bf16lo_f(rv[i].w); v[i * 8 + 7] += bf16hi_f(rv[i].w);
-                    }
-                }
-                if (GENERIC || DET != 0) {
-                    if (k_det == YL_DET_CLS_FILTER)
-                        det_filter_chunk<CW>(p, v, c, w0 + row, lane, det_best, det_bestc);
-                    else if (k_det)
-                        det_decode_chunk<CW>(p, v, c, w0 + row, det_dist, k_det);
-                }
-                if (!k_store) continue;
-                if (leader && g == 0 && lt == 0 && c < 2) YL_STAMP(c == 0 ? 9 : 13);
-                if (u == 0) {
-                    // the staging tile about to be overwritten must have been drained by its last TMA store:
-                    // every committed store has (two tiles: the newest committed one used this tile, the one
-                    // filled last is still pending; one tile: the newest committed one used it)
-                    if (leader) bulk_wait_read<0>();
-                    named_bar_sync(1 + g, kEpiGroupThreads);
-                    // ... and the barrier also says every thread has written + fenced the pending tile
-                    if (pend) {
-                        if (leader) {
-                            for (int m = p.y_map_first; m < p.y_map_last; ++m)
-                                tma_store_4d(&p.tmY[m], stg + pbuf, pc0, pw0, ph0, pi0);
-                            bulk_commit();
-                        }
-                        pend = 0;
-                    }
-                    if (leader && g == 0 && lt == 0 && (c == 0 || c == 2)) YL_STAMP(c == 0 ? 10 : 15);
-                }
-                const uint32_t base_off = row_off + (uint32_t)u * sub_bytes;
-                if (k_f32) {
-#pragma unroll
-                    for (int j = 0; j < CW / 4; ++j) {
-                        uint32_t off = base_off + (uint32_t)j * 16u;
-                        off ^= ((off >> 7) & swz_mask) << 4;   // fp32 rows of 128 B: a chunk may start a new line
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + buf + off),
-                                     "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                                     : "memory");
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < CW / 8; ++j) {
-                        const uint32_t off = (base_off + (uint32_t)j * 16u) ^ swz_xor;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + buf + off),
-                                     "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
-                                     "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
-                                     "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
-                                     "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
-                                     : "memory");
-                    }
-                }
-            }
-            if (!k_store) continue;
-            fence_proxy_async_smem();
-            if (leader && g == 0 && lt == 0 && s == 0) YL_STAMP(11);
-            if (dbl) {
-                pend = 1;
-                pbuf = buf;
-                pc0 = n0 + s * stg_sub * CW;
-                pw0 = w0;
-                ph0 = h0;
-                pi0 = i0;
-            } else {
-                named_bar_sync(1 + g, kEpiGroupThreads);
-                if (leader) {
-                    for (int m = p.y_map_first; m < p.y_map_last; ++m)
-                        tma_store_4d(&p.tmY[m], stg, n0 + s * stg_sub * CW, w0, h0, i0);
-                    bulk_commit();
-                }
-            }
-        }
-    }
-    if (dbl) {
-        named_bar_sync(1 + g, kEpiGroupThreads);
-        if (leader && pend) {
-            for (int m = p.y_map_first; m < p.y_map_last; ++m) tma_store_4d(&p.tmY[m], stg + pbuf, pc0, pw0, ph0, pi0);
-            bulk_commit();
-        }
-    }
-    if (leader && g == 0) YL_STAMP(5);
-    // the staging tiles must outlive the TMA engine's reads of them; the global writes themselves are flushed by
-    // the grid's completion (which is what the next kernel's griddepcontrol.wait / stream order waits for)
-    if (leader) bulk_wait_read<0>();
-    if (leader && g == 0) YL_STAMP(6);
-}
 
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
 // tile boundaries (the smem ring never drains), and with two TMEM accumulator stages the epilogue of tile i
@@ -647,6 +272,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         const int gtid = (e & 3) * 32 + lane;
         uint8_t* stg = sStg + (size_t)g * p.stg_bufs * p.stg_bytes;
+        const TileRange tr = {(int)blockIdx.x, p.total_tiles, (int)gridDim.x};
+        uint32_t acc_uses = 0;
         // epi_kind: 0 / 1 = the hot instantiations (32-column chunks, bf16 NHWC store, SiLU, without / with residual),
         // 2 = every other combination
         // epi_kind (host side, plan_conv_tc): the hot combinations get their own instantiation (32-column chunks):
@@ -654,7 +281,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         //   4 / 5 / 6  Detect box decode / class decode / class filter WITHOUT an NHWC store (engine path head convs)
         //   7  everything else (fp32 destination, decode + raw store, 16-column chunks)
 #define YL_EPI(CW_, ACT_, RES_, DET_, GEN_) \
-    conv_tc_epilogue<CW_, ACT_, RES_, DET_, GEN_, DBG>(p, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, stg, sbias)
+    conv_tc_epilogue<CW_, ACT_, RES_, DET_, GEN_, DBG>(p, p, tr, acc_uses, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, \
+                                                       stg, sbias)
         const int kind = DBG ? 7 : p.epi_kind;     // the timeline build keeps only the generic code
         if (kind == 0) YL_EPI(32, true, false, 0, false);
         else if (kind == 1) YL_EPI(32, true, true, 0, false);
@@ -831,6 +459,7 @@ static int env_int(const char* name, int dflt) {
 // Tuning knobs (A/B switches used by tools/): read from the environment ONCE, in yl_init; launches never touch getenv.
 struct ConvTcKnobs {
     int nsplit = 1, patch = 1, patch_k64 = 0, patch_wmax_kb = 80, small_nsplit = 1, patch_pitch = 10, patch_bo = 0;
+    int chain_nsplit = 1, chain_patch = 1, chain_bres = 1;
     int wres = 1, stg_sub = 2, stg_bufs = 2, wearly = 1, grid_ctas = 2, patch_eff_pct = 60;
 };
 static ConvTcKnobs g_knobs;
@@ -849,12 +478,15 @@ static void read_knobs() {
     k.wearly = env_int("YL_WEARLY", k.wearly);
     k.grid_ctas = env_int("YL_GRID_CTAS", k.grid_ctas);
     k.patch_eff_pct = env_int("YL_PATCH_EFF", k.patch_eff_pct);
+    k.chain_nsplit = env_int("YL_CHAIN_NSPLIT", k.chain_nsplit);
+    k.chain_patch = env_int("YL_CHAIN_PATCH", k.chain_patch);
+    k.chain_bres = env_int("YL_CHAIN_BRES", k.chain_bres);
     g_knobs = k;
 }
 
 // Everything of a launch that is decided on the host: tiling, mode (flat / halo patch / resident weights / N split),
 // smem carve-up and the tensor maps.  Shared by the launch and by yl_conv_tc_info (tests assert which path ran).
-static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* smem_out) {
+int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* smem_out, const ConvTcPlanOpts* opts) {
     char why[128];
     YL_CHECK(conv_tc_supported(a, why, sizeof(why)), YL_ERR_UNSUPPORTED, "tcgen05 conv unsupported: %s", why);
     const yl_tensor& x = a->x;
@@ -870,6 +502,10 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
                  "y_up dims mismatch: got (%d,%d,%d) expected (%d,%d,%d)", a->y_up.n, a->y_up.h, a->y_up.w, x.n, 2 * Ho,
                  2 * Wo);
 
+    const bool chain = opts && opts->chain;
+    if (chain)
+        YL_CHECK(!a->det.pred && y.data && y.dtype == YL_BF16, YL_ERR_UNSUPPORTED,
+                 "a conv chain takes bf16 -> bf16 layers without a Detect epilogue");
     memset(&p, 0, sizeof(p));
     p.ksize = a->k;
     p.stride = a->stride;
@@ -884,14 +520,14 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
 
     // N tiling
     const int co16 = ceil_div(y.c, 16) * 16;
-    int n_tiles = ceil_div(co16, 256);
+    int n_tiles = ceil_div(co16, chain ? 128 : 256);
     // A 129..256-wide tile needs all 512 TMEM columns for its two accumulator stages, i.e. one CTA per SM.  When the
     // M tiling then yields between one and two waves of CTAs (20x20 maps at bs = 64: 200 tiles on 148 SMs), the
     // second wave runs almost alone; halving the tile (2 CTAs/SM, 256 columns each) keeps every tile resident at once.
     {
         const long long m_est = ceil_div64((long long)x.n * Ho * Wo, 128);
         // (the class-filter epilogue needs every class of a pixel in ONE tile)
-        if (n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && g_knobs.nsplit &&
+        if (!chain && n_tiles == 1 && co16 > 128 && m_est > g_num_sms && m_est <= 2ll * g_num_sms && g_knobs.nsplit &&
             a->det.mode != YL_DET_CLS_FILTER)
             n_tiles = 2;
     }
@@ -900,7 +536,7 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     // halo-patch mode: 3x3 stride-1 convs on thin inputs are L2->SM bound when every tap is fetched separately
     // (9 narrow TMA boxes per tile); fetch the (TH+2) x (TW+2) patch once instead and slide the A descriptor
     bool patch = false;
-    if (a->k == 3 && a->stride == 1 && x.c <= 64 && n_tiles == 1 && g_knobs.patch) {
+    if (!chain && a->k == 3 && a->stride == 1 && x.c <= 64 && n_tiles == 1 && g_knobs.patch) {
         const int kb = g_knobs.patch_k64 ? 64 : p.kblk;
         const double eff = (double)Ho * Wo / ((double)ceil_div(Wo, 8) * 8 * ceil_div(Ho, 16) * 16);
         if (9 * p.co_tile * kb * 2 <= g_knobs.patch_wmax_kb * 1024 && eff * 100.0 >= (double)g_knobs.patch_eff_pct) {
@@ -912,7 +548,7 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     // Small problems (bs = 1 latency): with far fewer 128-pixel tiles than SMs a CTA's epilogue walks its N / 32 column
     // chunks serially (~0.45 us each, tools/timeline.py) while most of the GPU idles.  Split N down to 32-column tiles:
     // the chunks become parallel CTAs (the A tile is re-read from L2 by each, which is free at this size).
-    if (!patch && g_knobs.small_nsplit && (a->det.mode == YL_DET_NONE || a->det.mode == YL_DET_CLS)) {
+    if (!chain && !patch && g_knobs.small_nsplit && (a->det.mode == YL_DET_NONE || a->det.mode == YL_DET_CLS)) {
         const long long m_est = ceil_div64((long long)x.n * Ho * Wo, 128);
         int nt = n_tiles;
         while (m_est * nt * 2 <= g_num_sms && co16 % (64 * nt) == 0 && co16 / (2 * nt) >= 32) nt *= 2;
@@ -926,7 +562,7 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     // M tiling + activation tensor maps
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(x.data) + x.coff;
     const uint64_t es = 2;
-    const bool flat = (a->k == 1 && a->stride == 1 && !a->upsample2x && !a->y_up.data);
+    const bool flat = (!chain && a->k == 1 && a->stride == 1 && !a->upsample2x && !a->y_up.data);
     if (patch) {
         p.patch = 1;
         p.patch_pw = g_knobs.patch_pitch;
@@ -973,11 +609,33 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
         p.Ho = Ho;
         p.Wo = Wo;
         p.Nimg = x.n;
-        choose_patch(Ho, Wo, x.n, &p.TH, &p.TW, &p.TN);
+        choose_patch(Ho, Wo, chain ? 1 : x.n, &p.TH, &p.TW, &p.TN);
+        if (chain && g_knobs.chain_nsplit) {
+            // a cluster of `chain_cluster` CTAs owns one image: give every CTA (at least) two tiles per layer when the
+            // channel count allows, so both epilogue groups of a CTA drain an accumulator at the same time
+            const int tm = ceil_div(Ho, p.TH) * ceil_div(Wo, p.TW);
+            // (1x1 only: every extra N tile of a 3x3 re-reads the nine shifted A boxes, and those layers are bound by
+            // L2 -> SM traffic, tools/chain_timeline.py)
+            while (a->k == 1 && tm * n_tiles < 2 * opts->chain_cluster && co16 % (64 * n_tiles) == 0 &&
+                   co16 / (2 * n_tiles) >= 32)
+                n_tiles *= 2;
+            p.co_tile = ceil_div(ceil_div(co16, n_tiles), 16) * 16;
+        }
+        // chain, 3x3 stride 1: "full-width patch".  The M rows of a tile are (TW = Wo + 2) x TH consecutive positions of a
+        // zero-padded (Wo + 2)-wide image, so tap (r, s) of the whole tile is the SAME shared-memory patch read from a start
+        // address shifted by r * TW + s rows: ONE TMA box {kblk, Wo + 2, TH + 2} per tile and channel block instead of nine
+        // (these layers are bound by L2 -> SM bytes and by the TMA box-row rate, not by math).  The two surplus columns of
+        // every row compute junk that the destination tensor map clips (columns Wo, Wo + 1 are out of bounds).
+        if (chain && a->k == 3 && a->stride == 1 && Wo + 2 <= 128 && p.cin_blocks <= 2 && g_knobs.chain_patch) {
+            p.ch_mode = 1;
+            p.TW = Wo + 2;
+            p.TH = 128 / p.TW < Ho ? 128 / p.TW : Ho;
+            p.TN = 1;
+        }
         p.tiles_h = ceil_div(Ho, p.TH);
         p.tiles_w = ceil_div(Wo, p.TW);
         p.tiles_n = ceil_div(x.n, p.TN);
-        uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.TW, (uint32_t)(p.ch_mode ? p.TH + 2 : p.TH), (uint32_t)p.TN};
         if (a->stride == 1) {
             uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
             uint64_t str[3] = {(uint64_t)x.cstride * es, (uint64_t)x.cstride * es * x.w,
@@ -1019,6 +677,13 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
         p.w_bytes = 9u * p.co_tile * p.kblk * 2u;
         p.b_bytes = (p.w_bytes + 1023u) & ~1023u;
     }
+    if (chain) {
+        const uint32_t rb = (uint32_t)p.kblk * 2u;
+        p.ch_a_tx = (uint32_t)(p.TW * (p.ch_mode ? p.TH + 2 : p.TH) * p.TN) * rb;
+        p.ch_b_tx = (uint32_t)p.co_tile * rb;
+        // the last tap of accumulator row 127 reads patch row 127 + 2 * TW + 2
+        if (p.ch_mode) p.a_bytes = ((uint32_t)(130 + 2 * p.TW) * rb + 1023u) & ~1023u;
+    }
     p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.n_tiles = n_tiles;
     p.total_tiles = p.m_tiles * n_tiles;
@@ -1032,10 +697,11 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     YL_CHECK(cols <= 512, YL_ERR_UNSUPPORTED, "accumulator needs %u TMEM columns", cols);
     p.tmem_cols = cols;
     int ctas_per_sm = (cols <= 256) ? 2 : 1;
+    if (chain) YL_CHECK(cols <= 256, YL_ERR_UNSUPPORTED, "chain layer needs %u TMEM columns (two CTAs share an SM)", cols);
     if (patch && p.b_bytes > 40u * 1024u) ctas_per_sm = 1;  // big resident 9-tap weights: one CTA owns the SM
     const int kiters_total = a->k * a->k * p.cin_blocks;
     const size_t wres_bytes = (size_t)kiters_total * p.b_bytes;
-    if (!patch && n_tiles == 1 && g_knobs.wres &&
+    if (!chain && !patch && n_tiles == 1 && g_knobs.wres &&
         wres_bytes <= (size_t)(ctas_per_sm == 2 ? 48 : 120) * 1024) {
         p.wres = 1;
         p.w_bytes = (uint32_t)kiters_total * (uint32_t)p.co_tile * p.kblk * 2u;
@@ -1044,7 +710,8 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
     const int nbias = n_tiles * p.co_tile + 32;
     const uint32_t stage_bytes = (patch || p.wres) ? p.a_bytes : p.a_bytes + p.b_bytes;
     const size_t fixed_b = patch ? p.b_bytes : (p.wres ? wres_bytes : 0);
-    const size_t cta_smem = (size_t)(ctas_per_sm == 2 ? 112 * 1024 : 224 * 1024);
+    // (a chain CTA also keeps two copies of the parameter block and its barriers in front of the operand ring)
+    const size_t cta_smem = chain ? (size_t)(112 * 1024 - 5632) : (size_t)(ctas_per_sm == 2 ? 112 * 1024 : 224 * 1024);
 
     // staging: prefer 128-B pixel rows per TMA store (two TMEM chunks of bf16) and two staging tiles per
     // epilogue group (the store of chunk k overlaps chunk k+1); fall back when the operand ring would get
@@ -1063,15 +730,53 @@ static int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, s
         p.stg_bytes = (128u * (uint32_t)p.stg_row_bytes + 1023u) & ~1023u;  // 128 rows; 1024-B swizzle atoms
         fixed = 1024 + 2 * (size_t)p.stg_bufs * p.stg_bytes + (size_t)((nbias + 3) & ~3) * 4 + 16;
         const long long budget = (long long)cta_smem - (long long)fixed - (long long)fixed_b - 16 * 24 - 64;
+        if (chain) {
+            // two rings: activations (ring A: one stage per k-iteration, or per (tile, channel block) patch) and weights
+            // (ring B: one stage per k-iteration, or RESIDENT for the layer: a CTA of the cluster only ever sees one N
+            // tile when n_tiles divides the cluster size, so its k-iterations' weight tiles are loaded once per layer)
+            const int cs = opts->chain_cluster;
+            const int kit = a->k * a->k * p.cin_blocks;
+            const int a_set = p.ch_mode ? p.cin_blocks : 1;
+            const int tiles_cta = ceil_div(p.tiles_w * p.tiles_h * n_tiles, cs);
+            const long long ab = p.a_bytes, bb = p.b_bytes;
+            int na = 0, nb = 0, bres = 0;
+            if (g_knobs.chain_bres && cs % n_tiles == 0 && (long long)kit * bb + a_set * ab <= budget) {
+                bres = 1;
+                nb = kit;
+                na = (int)((budget - (long long)kit * bb) / ab);
+                const int sets = tiles_cta > 1 ? 2 : 1;
+                if (p.ch_mode) na = (na / a_set < sets ? na / a_set : sets) * a_set;
+                else if (na > 6) na = 6;
+                if (!p.ch_mode && na < 2 && tiles_cta * kit > 1) bres = 0;   // a one-deep activation ring would serialise the loads
+            }
+            if (bres) {
+            } else if (p.ch_mode) {
+                na = a_set * ((tiles_cta > 1 && 2 * a_set * ab + 3 * bb <= budget) ? 2 : 1);
+                nb = (int)((budget - na * ab) / bb);
+                if (nb > 12) nb = 12;
+            } else {
+                na = nb = (int)(budget / (ab + bb));
+                if (na > 6) na = nb = 6;
+            }
+            const bool ok = na >= a_set && na >= 1 && (bres || nb >= 2) && (p.ch_mode || bres || na >= 2);
+            p.ch_na = na;
+            p.ch_nb = nb;
+            p.ch_bres = bres;
+            stages = ok ? (na > 2 ? na : 2) : 0;
+            if (ok) break;
+            continue;
+        }
         stages = budget > 0 ? (int)(budget / stage_bytes) : 0;
         if (stages >= 3 || (stages >= 2 && (size_t)stages * stage_bytes >= 40 * 1024)) break;
     }
     p.nstore = ceil_div(p.nchunks, p.stg_sub);
+    if (chain) YL_CHECK(stages > 0, YL_ERR_UNSUPPORTED, "chain layer does not fit the shared-memory budget");
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.b_region = (uint32_t)((patch || p.wres) ? fixed_b : (size_t)stages * p.b_bytes);
-    const size_t smem = fixed + fixed_b + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 16;
+    const size_t smem = chain ? fixed + (size_t)p.ch_na * p.a_bytes + (size_t)p.ch_nb * p.b_bytes + 64
+                              : fixed + fixed_b + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 16;
     YL_CHECK((int)smem <= g_max_dyn_smem, YL_ERR_UNSUPPORTED, "conv tile needs %zu B smem (max %d)", smem,
              g_max_dyn_smem);
 

@@ -105,6 +105,13 @@ class ConvTcPlan(C.Structure):
                                          "co_tile", "kblk", "stages", "grid", "smem_bytes", "tmem_cols")]
 
 
+class ConvChain(C.Structure):
+    """Mirror of `yl_conv_chain` (a built chain of conv layers: yl_conv_chain_build / yl_conv_chain_run)."""
+
+    _fields_ = [("desc", C.c_void_p)] + [(k, C.c_int32) for k in ("n_layers", "batch", "cluster", "smem_bytes",
+                                                                   "tmem_cols", "reserved")]
+
+
 _PROTOTYPES = {
     "yl_version": (C.c_int, []),
     "yl_last_error_string": (C.c_char_p, []),
@@ -119,6 +126,12 @@ _PROTOTYPES = {
     "yl_conv_bn_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "yl_conv_tc_supported": (C.c_int, [C.POINTER(ConvArgs)]),
     "yl_conv_tc_info": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvTcPlan)]),
+    "yl_conv_chain_desc_bytes": (C.c_size_t, [C.c_int]),
+    "yl_conv_chain_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "yl_conv_chain_build": (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p, C.c_size_t, C.POINTER(ConvChain),
+                                      C.c_void_p]),
+    "yl_conv_chain_run": (C.c_int, [C.POINTER(ConvChain), C.c_void_p]),
+    "yl_conv_chain_debug": (C.c_int, [C.c_void_p]),
     "yl_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                C.POINTER(Tensor), C.c_int, C.c_void_p]),
     "yl_dwconv3x3": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_int,

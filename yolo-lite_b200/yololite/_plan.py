@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 from typing import Callable
 
 import torch
@@ -73,6 +74,13 @@ class Builder:
         # filter in its conv epilogues (set by BaseModel._get_plan); the head then fills `cand_ws`
         self.nms_fuse_conf: float | None = None
         self.cand_ws: torch.Tensor | None = None
+        # conv chains (csrc/conv_chain.cu): runs of small-map convs as ONE launch, one 4-CTA cluster per image.  Opt-in
+        # (YL_CHAIN=1): parity-exact, but measured 3-5 % slower than the per-layer launches at every batch size — those
+        # layers are bound by L2 -> SM operand traffic and the per-MMA A-operand read, not by launch overhead
+        # (profiles/r02_conv_chain.md)
+        self.chain_enabled = os.environ.get("YL_CHAIN", "0") == "1"
+        self.chain_min_batch = int(os.environ.get("YL_CHAIN_MIN_BATCH", "1"))
+        self.chain_max_hw = int(os.environ.get("YL_CHAIN_MAX_HW", "1600"))
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -344,7 +352,74 @@ class Builder:
                    bytes_=x.n * x.h * x.w * x.c * (x.buf.element_size() + 4), reads=(x,), writes=(out,))
         return out
 
+    # ------------------------------------------------------------------ conv chains
+    def _fuse_chains(self):
+        """Merge runs of consecutive small-map conv launches of one lane into yl_conv_chain launches (one cluster per
+        image walks the whole run; csrc/conv_chain.cu).  Members keep their order, so every dependency inside a run is
+        satisfied by the chain's own layer barriers; the chain inherits the members' outside dependencies."""
+        n = len(self.calls)
+        lib = self.lib
+
+        def member(i):
+            fn, args, keep = self.calls[i]
+            if fn is not lib.yl_conv_bn_act or self.meta[i]["kind"] != "conv_tc":
+                return False
+            a = keep[0]
+            if a.x.n < self.chain_min_batch or a.y.h * a.y.w > self.chain_max_hw or a.x.h * a.x.w > self.chain_max_hw:
+                return False
+            return bool(lib.yl_conv_chain_supported(C.byref(a)))
+
+        ok = [member(i) for i in range(n)]
+        groups, i = [], 0
+        while i < n:
+            if not ok[i]:
+                i += 1
+                continue
+            j = i
+            while j + 1 < n and ok[j + 1] and self.lanes[j + 1] == self.lanes[i]:
+                j += 1
+            if j > i:
+                groups.append((i, j))
+            i = j + 1
+        if not groups:
+            return
+        start = {g[0]: g for g in groups}
+        new_index, calls, lanes, deps, meta = {}, [], [], [], []
+        i = 0
+        while i < n:
+            if i in start:
+                lo, hi = start[i]
+                idx = len(calls)
+                for m in range(lo, hi + 1):
+                    new_index[m] = idx
+                members = list(range(lo, hi + 1))
+                arr = (_C.ConvArgs * len(members))(*[self.calls[m][2][0] for m in members])
+                nbytes = int(lib.yl_conv_chain_desc_bytes(len(members)))
+                desc = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                chain = _C.ConvChain()
+                _C.check(lib.yl_conv_chain_build(arr, len(members), desc.data_ptr(), nbytes, C.byref(chain),
+                                                 _C.stream_ptr()), "yl_conv_chain_build")
+                self.buffers.append(desc)
+                calls.append((lib.yl_conv_chain_run, (C.byref(chain),),
+                              (chain, desc, arr, [self.calls[m][2] for m in members])))
+                lanes.append(self.lanes[lo])
+                deps.append(tuple(sorted({new_index[d] for m in members for d in self.deps[m] if d < lo})))
+                mm = [self.meta[m] for m in members]
+                meta.append({"kind": "conv_chain", "bytes": sum(x["bytes"] for x in mm), "flops": sum(x["flops"] for x in mm),
+                             "desc": f"{len(mm)} convs: " + " | ".join(x["desc"] for x in mm), "members": mm})
+                i = hi + 1
+            else:
+                new_index[i] = len(calls)
+                calls.append(self.calls[i])
+                lanes.append(self.lanes[i])
+                deps.append(tuple(sorted({new_index[d] for d in self.deps[i]})))
+                meta.append(self.meta[i])
+                i += 1
+        self.calls, self.lanes, self.deps, self.meta = calls, lanes, deps, meta
+
     def finish(self) -> "Plan":
+        if self.chain_enabled:
+            self._fuse_chains()
         return Plan(self)
 
 
