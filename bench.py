@@ -522,10 +522,10 @@ def main():
             return int(c.sum()), d.nbytes + c.nbytes
 
         def e2e_run(host_batches, label):
-            for i in range(3):
+            for i in range(max(3, steps_e // 2)):              # warm-up: plan build, pinned pages, copy-engine queues
                 read_all(yl.predict(host_batches[i % n_sets], **kw))
             best = None
-            for _ in range(3):                                  # 3 x steps_e steps; the median run is reported
+            for _ in range(5):                                  # 5 x steps_e steps; the median run is reported
                 barrier()
                 t0 = time.perf_counter()
                 nd, d2h = 0, 0
