@@ -313,6 +313,55 @@ def test_infer_nms_equals_infer_then_nms():
         assert torch.equal(c1, c2)
 
 
+def test_fused_class_filter_tie_rules_match_the_score_path():
+    """The class filter in the head-conv epilogue picks the best class from the LOGITS (one sigmoid per pixel); the
+    reference's rule is `scores.max(1)` = the FIRST class whose SCORE is maximal.  Crafted class weights put exact ties
+    (identical rows), near ties (rows whose logits differ by 1e-7 .. 1e-3: some round to the same score, some do not),
+    saturated scores (logits > 5 and > 17, where all scores are 1.0) and far-negative logits into every pixel: the fused
+    path must still equal `infer()` + `nms_padded()` (which reads the stored scores) bit for bit."""
+    import numpy as np
+    import torch
+
+    from oracle.weights import fill_state_dict_
+    from yololite.nn.tasks import DetectionModel
+    from yololite.utils import ops
+
+    m = fill_state_dict_(DetectionModel("yolo11n.yaml", verbose=False)).eval()
+    det = m.model[-1]
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for lvl, seq in enumerate(det.cv3):
+            w, b = seq[-1].weight, seq[-1].bias            # (nc, c3, 1, 1), (nc,)
+            b.copy_(torch.randn(b.shape, generator=g) * 1.0 - 3.0)
+            w[40], b[40] = w[12], b[12]                    # exact tie: class 12 must win over 40
+            w[41], b[41] = w[12], b[12] + 1e-7             # near ties around the rounding width of the score
+            w[42], b[42] = w[12], b[12] + 1e-6
+            w[43], b[43] = w[12], b[12] + 1e-5
+            w[5], b[5] = w[12], b[12] + 1e-4               # ... with the LARGER logit at the LOWER index as well
+            w[44], b[44] = w[12], b[12] + 1e-3
+            if lvl == 1:                                   # saturation: sigmoid(v) == 1.0f for both, first index wins
+                b[20] = 30.0
+                b[60] = 40.0
+            if lvl == 2:                                   # scores in (sigmoid(5), 1): the slow path by rule
+                b[33] = 9.0
+                w[34], b[34] = w[33], b[33] + 2e-6
+                b[70] = -120.0                             # e^-v overflows: score 0
+    m = m.cuda()
+    x = torch.rand(4, 3, 160, 96, generator=torch.Generator().manual_seed(5)).cuda()
+    for conf in (0.001, 0.25, 0.9):
+        y, _ = m.infer(x)
+        d0, c0 = ops.nms_padded(y.clone(), conf, 0.7, None, False, False, 300)
+        d1, c1 = m.infer_nms(x, conf=conf, iou=0.7)
+        torch.cuda.synchronize()
+        assert torch.equal(c0, c1), (conf, c0.tolist(), c1.tolist())
+        assert int(c0.sum()) > 0
+        for i, n in enumerate(c0.tolist()):
+            assert np.array_equal(d0[i, :n].cpu().numpy(), d1[i, :n].cpu().numpy()), (conf, i)
+    # the crafted classes are really what the detections carry (the test would be vacuous otherwise)
+    cls = set(d1[..., 5].flatten().tolist())
+    assert 12.0 in cls or 5.0 in cls or 20.0 in cls or 33.0 in cls, sorted(cls)[:10]
+
+
 # ------------------------------------------------------------------------------------------------ benchmark shapes
 def _oracle_forward_chunked(sd, x, chunk=16):
     from oracle import yolo11_ref

@@ -125,14 +125,43 @@ __device__ __forceinline__ void det_filter_chunk(const ConvTcParams& p, const fl
         best = -INFINITY;
         bestc = 0;
     }
+    // The sigmoid is monotone, so the best class of the chunk is where the LOGIT is largest: two passes of min / max /
+    // compare instead of 2 MUFU ops per class (the epilogue of these layers was MUFU-bound), then ONE sigmoid.  What a
+    // monotone map does not preserve is the reference's tie rule (the FIRST class whose SCORE is maximal wins, also when
+    // its logit is a hair smaller but rounds to the same score).  Ties in the score need the two largest logits within
+    // `eps` of each other (bound derived from the error of ex2.approx / rcp.approx and the rounding of 1 + e^-v; scores
+    // above sigmoid(5) sit where 1 + e^-v loses the difference): then, for the whole warp, the per-class evaluation below
+    // decides exactly as before.  Random logits take that path for < 1 % of the warps.
+    float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
-        const int ch = c * CW + i;
-        if (ch < p.det_nc) {
-            const float sc = __fdividef(1.f, 1.f + __expf(-v[i]));   // the value YL_DET_CLS would have stored
-            if (sc > best) {
-                best = sc;
-                bestc = ch;
+        if (c * CW + i < p.det_nc) {
+            m2 = fmaxf(m2, fminf(m1, v[i]));
+            m1 = fmaxf(m1, v[i]);
+        }
+    }
+    const float eps = m1 <= 0.f ? 2e-6f * fmaxf(8.f, -m1) : 1e-3f;
+    const bool unsure = !(m1 <= 5.f) || !(m2 < m1 - eps);      // (NaN / -inf logits land here too)
+    if (!__any_sync(0xffffffffu, unsure)) {
+        int idx = 0;
+#pragma unroll
+        for (int i = CW - 1; i >= 0; --i)
+            if (v[i] == m1) idx = i;                            // (lanes beyond nc never equal m1: it came from a valid one)
+        const float sc = __fdividef(1.f, 1.f + __expf(-m1));    // the value YL_DET_CLS would have stored
+        if (sc > best) {
+            best = sc;
+            bestc = c * CW + idx;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+            const int ch = c * CW + i;
+            if (ch < p.det_nc) {
+                const float sc = __fdividef(1.f, 1.f + __expf(-v[i]));
+                if (sc > best) {
+                    best = sc;
+                    bestc = ch;
+                }
             }
         }
     }
