@@ -192,6 +192,15 @@ int yl_stem_conv(const float* x_nchw, int n, int ci, int h, int w, const void* w
 int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const float* bias, int act,
                  const yl_tensor* add, void* stream);
 
+/* DWConv 3x3 + Conv 1x1 as one launch (csrc/dwpw_tc.cu): `nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1))` of the Detect class
+ * branch (head.py:46-47), i.e. conv.py:100-105 followed by conv.py:47-49.  The depthwise conv (+ folded BN + SiLU) runs on
+ * CUDA cores inside the producer of the 1x1 GEMM's A operand (depthwise result -> swizzled shared-memory tile -> tcgen05.mma),
+ * so the intermediate tensor is never written.  `pw` describes the 1x1 conv whose `x` is the DEPTHWISE INPUT (same
+ * dims as the depthwise output); dw_w is bf16 [9][x.c], dw_bias f32 [x.c] (yl_fold_bn_pack with depthwise = 1).
+ * Needs x.c % 16 == 0, x.c <= 256, y.c <= 128, no residual / upsample / Detect epilogue. */
+int yl_dw_pw_supported(const yl_conv_args* pw);
+int yl_dw_pw_conv(const yl_conv_args* pw, const void* dw_w, const float* dw_bias, int dw_act, void* stream);
+
 /* SPPF's three chained MaxPool2d(5,1,2) (block.py:182-184), -inf padding; y1=m(x), y2=m(y1), y3=m(y2). */
 int yl_sppf_pool(const yl_tensor* x, const yl_tensor* y1, const yl_tensor* y2, const yl_tensor* y3, int k,
                  void* stream);

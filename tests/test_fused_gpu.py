@@ -257,3 +257,76 @@ def test_model_with_chains_equals_model_without(monkeypatch):
     assert not [md for md in metas["0"] if md["kind"] == "conv_chain"]
     small = [md for md in metas["1"] if md["kind"] == "conv_tc" and ("20x20" in md["desc"] or "40x40" in md["desc"])]
     assert len(small) <= 8, [md["desc"] for md in small]      # what remains: the Detect head's last 1x1 convs
+
+
+# ------------------------------------------------------------------------------------------------ DWConv 3x3 + Conv 1x1
+@pytest.mark.parametrize("c,co,n,h,w,coff", [
+    (64, 80, 2, 24, 40, 0),      # 80x80-level shape class: one channel block, ragged tile rows / columns
+    (80, 80, 1, 17, 23, 0),      # a 64 + 16 channel split, odd sizes: partial tiles both ways
+    (128, 80, 2, 40, 40, 16),    # two channel blocks, destination is a channel slice
+    (256, 80, 3, 20, 20, 0),     # four channel blocks (the 20x20 level)
+    (16, 32, 1, 8, 16, 0),       # one narrow block, exactly one tile
+    (96, 128, 1, 12, 20, 0),     # 64 + 32 split, 128 output channels
+])
+def test_dw_pw_fused_vs_layerwise_and_fp32(c, co, n, h, w, coff):
+    """yl_dw_pw_conv (depthwise 3x3 inside the A-operand producer of the 1x1 tcgen05 GEMM) against the two layers launched
+    one by one and against fp32 PyTorch on the CPU; bytes around a channel-slice destination stay untouched."""
+    from yololite import _plan
+    from yololite._ops import View
+    from yololite.nn.modules import Conv, DWConv
+    from yololite.nn.modules.head import Detect
+
+    seq = torch.nn.Sequential(_randomise_bn(DWConv(c, c, 3), 21 + c), _randomise_bn(Conv(c, co, 1), 22 + co)).eval().cuda()
+    x = torch.rand(n, c, h, w, generator=torch.Generator().manual_seed(13)) * 2 - 1
+    xb = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    dev = torch.device("cuda", 0)
+    outs = {}
+    for mode in ("fused", "layers"):
+        g = _plan.Builder(dev)
+        g.dwpw_enabled = mode == "fused"
+        big = g.alloc(n, h, w, co + 2 * coff)
+        big.buf.fill_(7.5)
+        dest = big.slice(coff, co)
+        if mode == "fused":
+            dw, pw = seq[0], seq[1]
+            from yololite.nn.modules._emit import act_flag, packed
+
+            y = g.dwpw(View(xb, 0, c), packed(dw.conv, dw.bn, dw), act_flag(dw.act), packed(pw.conv, pw.bn, pw),
+                       act_flag(pw.act), out=dest)
+            assert y is not None, "the fused kernel rejected a supported shape"
+            assert [md["kind"] for md in g.meta] == ["dwpw_tc"]
+        else:
+            t = seq[0]._emit(g, View(xb, 0, c))
+            seq[1]._emit(g, t, out=dest)
+            assert [md["kind"] for md in g.meta] == ["dwconv3x3", "conv_tc"]
+        plan = g.finish()
+        plan.run_eager()
+        plan.run_eager()
+        torch.cuda.synchronize()
+        outs[mode] = big.buf.clone()
+        if coff:
+            assert (big.buf[..., :coff] == 7.5).all() and (big.buf[..., coff + co:] == 7.5).all()
+    f = outs["fused"][..., coff:coff + co].float().cpu().permute(0, 3, 1, 2)
+    u = outs["layers"][..., coff:coff + co].float().cpu().permute(0, 3, 1, 2)
+
+    def ref_conv(cv, t):
+        yy = F.conv2d(t, cv.conv.weight.float().cpu(), None, cv.conv.stride, cv.conv.padding, 1, cv.conv.groups)
+        bn = cv.bn
+        yy = (yy - bn.running_mean.cpu()[None, :, None, None]) / torch.sqrt(bn.running_var.cpu()[None, :, None, None] + bn.eps)
+        return F.silu(yy * bn.weight.cpu()[None, :, None, None] + bn.bias.cpu()[None, :, None, None])
+
+    ref = ref_conv(seq[1], ref_conv(seq[0], xb.float().cpu().permute(0, 3, 1, 2)))
+    assert ((f - ref).abs() <= 4e-2 + 2e-2 * ref.abs()).all(), float((f - ref).abs().max())
+    assert float((f - u).abs().max()) <= 3e-2, float((f - u).abs().max())
+
+
+def test_detect_class_branch_uses_the_fused_dw_pw_kernel():
+    from bench import randomise_model_
+    from yololite.nn.tasks import DetectionModel
+
+    m = randomise_model_(DetectionModel("yolo11n.yaml", verbose=False)).eval().cuda()
+    x = torch.rand(1, 3, 64, 64, device="cuda")
+    m.infer(x)
+    kinds = [md["kind"] for md in m._get_plan(x.shape, x.device)[0].meta]
+    assert kinds.count("dwpw_tc") == 6, kinds           # 3 levels x 2 stages of the class branch
+    assert kinds.count("dwconv3x3") == 2, kinds          # what remains: Attention.pe of C2PSA

@@ -13,7 +13,7 @@ import sys
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-SOURCES = ["runtime.cu", "conv.cu", "conv_tc.cu", "conv_chain.cu", "conv_direct.cu", "layout.cu", "pool.cu", "attention.cu",
+SOURCES = ["runtime.cu", "conv.cu", "conv_tc.cu", "conv_chain.cu", "dwpw_tc.cu", "conv_direct.cu", "layout.cu", "pool.cu", "attention.cu",
            "decode.cu", "nms.cu", "preprocess.cu", "c3k2_fused.cu", "c3k2_tc.cu", "stem_fused.cu", "metrics.cu"]
 HEADERS = [HERE / "common.cuh", HERE / "conv_tc.cuh", HERE.parents[1] / "include" / "yl11.h"]
 OUT_DIR = HERE.parent / "yololite" / "lib"

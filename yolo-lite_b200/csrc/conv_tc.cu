@@ -325,7 +325,7 @@ int init_conv_tc() {
     return YL_OK;
 }
 
-static bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const uint64_t* dims,
+bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) {
@@ -345,7 +345,7 @@ static bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, void* base, int r
     return true;
 }
 
-static CUtensorMapSwizzle swizzle_for_bytes(int row_bytes) {
+CUtensorMapSwizzle swizzle_for_bytes(int row_bytes) {
     return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
@@ -424,7 +424,7 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
 
 // Tensor maps of a destination of conv-output resolution (Ho, Wo) [up == 0, one map] or of the 2x-upsampled
 // resolution [up == 1, four parity-plane maps]; flat mode describes the pixel axis as one dimension.
-static bool encode_out_maps(CUtensorMap* maps, const yl_tensor& y, int Ho, int Wo, int N, bool flat, bool up,
+bool encode_out_maps(CUtensorMap* maps, const yl_tensor& y, int Ho, int Wo, int N, bool flat, bool up,
                             const uint32_t* box, CUtensorMapSwizzle sw) {
     const uint64_t es = (y.dtype == YL_F32) ? 4 : 2;
     const CUtensorMapDataType dt = (y.dtype == YL_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;

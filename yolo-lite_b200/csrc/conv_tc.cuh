@@ -442,6 +442,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, const Co
 }
 
 // host side (conv_tc.cu)
+bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw);
+CUtensorMapSwizzle swizzle_for_bytes(int row_bytes);
+// tensor maps of a conv destination ([up == 0]: one map at conv resolution; [up == 1]: four parity planes of the 2x map)
+bool encode_out_maps(CUtensorMap* maps, const yl_tensor& y, int Ho, int Wo, int N, bool flat, bool up, const uint32_t* box,
+                     CUtensorMapSwizzle sw);
 struct ConvTcPlanOpts {
     int chain = 0;          // plan for conv_chain_kernel: tiles never span images (TN = 1, no flat mode), streamed weights only
                             // (no halo patch / resident weights), N tiles <= 128 columns (two CTAs per SM), no batch-size

@@ -33,6 +33,7 @@ bool pdl_enabled() { return g_pdl_env != 0 && t_pdl_user != 0; }
 
 int init_conv_tc();    // conv_tc.cu
 int init_conv_chain(); // conv_chain.cu
+int init_dwpw();       // dwpw_tc.cu
 int init_nms();        // nms.cu
 int init_attention();  // attention.cu
 int init_pool();       // pool.cu
@@ -85,6 +86,7 @@ int yl_init(int device) {
     int rc;
     if ((rc = yl::init_conv_tc()) != 0) return rc;
     if ((rc = yl::init_conv_chain()) != 0) return rc;
+    if ((rc = yl::init_dwpw()) != 0) return rc;
     if ((rc = yl::init_nms()) != 0) return rc;
     if ((rc = yl::init_attention()) != 0) return rc;
     if ((rc = yl::init_pool()) != 0) return rc;

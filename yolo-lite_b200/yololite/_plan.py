@@ -81,6 +81,8 @@ class Builder:
         self.chain_enabled = os.environ.get("YL_CHAIN", "0") == "1"
         self.chain_min_batch = int(os.environ.get("YL_CHAIN_MIN_BATCH", "1"))
         self.chain_max_hw = int(os.environ.get("YL_CHAIN_MAX_HW", "1600"))
+        # DWConv 3x3 + Conv 1x1 pairs (Detect class branch) as one launch (csrc/dwpw_tc.cu)
+        self.dwpw_enabled = os.environ.get("YL_DWPW", "1") != "0"
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -225,6 +227,25 @@ class Builder:
                            None if det is None or det.mode != _C.DET_CLS_FILTER else
                            (det.cand_ws, 1 + det.anchor0, 2 + det.anchor0)))
         return y if store else None
+
+    def dwpw(self, x: View, pdw: PackedConv, act_dw: bool, ppw: PackedConv, act_pw: bool, out=None):
+        """DWConv 3x3 (+BN+act) followed by Conv 1x1 (+BN+act) as one launch (yl_dw_pw_conv): the depthwise result feeds the
+        1x1 GEMM through shared memory and is never written.  Returns None when the fused kernel does not take the shape
+        (the caller then emits the two layers)."""
+        x = self.mat(x)
+        if not (self.dwpw_enabled and pdw.depthwise and pdw.k == 3 and ppw.k == 1 and not ppw.depthwise
+                and pdw.co == x.c and pdw.co_pad == x.c and ppw.ci == x.c):
+            return None
+        y = self._out(out, x.n, x.h, x.w, ppw.co)
+        a = _ops.conv_args(x, y, ppw, 1, act_pw, None, False, _C.IMPL_TCGEN05, None, None)
+        if not self.lib.yl_dw_pw_supported(C.byref(a)):
+            return None
+        px = x.n * x.h * x.w
+        self._push(self.lib.yl_dw_pw_conv, C.byref(a), pdw.w.data_ptr(), pdw.bias.data_ptr(), int(bool(act_dw)),
+                   keep=(a, pdw, ppw), kind="dwpw_tc", bytes_=px * (x.c + ppw.co) * 2 + (9 * x.c + x.c * ppw.co) * 2,
+                   flops=2 * px * (9 * x.c + x.c * ppw.co), desc=f"[dw3x3 {x.c}, {x.c}->{ppw.co} k1] {x.h}x{x.w}",
+                   reads=(x,), writes=(y,))
+        return y
 
     def stem_fused(self, x: NchwInput, pc0: PackedConv, pc1: PackedConv, act0: bool, act1: bool, out=None) -> View:
         """Image ingest + the first two stride-2 3x3 convs in one launch (see yl_stem_fused)."""

@@ -84,7 +84,8 @@ class Detect(YLModule):
             for i, x in enumerate(feats):
                 raw = g.alloc(x.n, x.h, x.w, self.no, dtype=torch.float32)
                 emit_any(g, self.cv2[i], x, out=raw.slice(0, nbox), out_dtype=torch.float32)
-                emit_any(g, self.cv3[i], x, out=raw.slice(nbox, self.nc), out_dtype=torch.float32)
+                emit_any(g, self.cv3[i][-1], self._emit_branch(g, self.cv3[i][:-1], x), out=raw.slice(nbox, self.nc),
+                         out_dtype=torch.float32)
                 raws.append(raw)
             y = g.detect_decode(raws, [float(s) for s in self.stride], self.reg_max, self.nc)
             return y, raws
@@ -113,7 +114,7 @@ class Detect(YLModule):
                 # them next to the rest of the neck (the last level's box branch stays on the main lane)
                 lane = 0 if (i == self.nl - 1 and j == 0) or not self.parallel_branches else 1 + 2 * i + j
                 with g.lane(lane):
-                    t = emit_any(g, branch[:-1], x)
+                    t = self._emit_branch(g, branch[:-1], x)
                     last = branch[-1]
                     if filt and mode == _C.DET_CLS:
                         det = _ops.DetEpilogue(y, _C.DET_CLS_FILTER, self.reg_max, self.nc, a0, float(self.stride[i]),
@@ -126,6 +127,23 @@ class Detect(YLModule):
                 raws.append(raw)
             a0 += x.h * x.w
         return y, raws
+
+    @staticmethod
+    def _emit_branch(g, mods, x):
+        """The convs of one head branch in front of its last 1x1.  A class-branch stage `Sequential(DWConv 3x3, Conv 1x1)`
+        (head.py:46-47) runs as ONE launch when the fused kernel takes the shape (yl_dw_pw_conv)."""
+        from ._emit import act_flag, packed
+
+        for sub in mods:
+            y = None
+            if (isinstance(sub, nn.Sequential) and len(sub) == 2 and isinstance(sub[0], DWConv) and type(sub[1]) is Conv
+                    and sub[0].conv.kernel_size == (3, 3) and sub[0].conv.stride == (1, 1)
+                    and sub[1].conv.kernel_size == (1, 1) and sub[1].conv.stride == (1, 1) and sub[1].conv.groups == 1):
+                dw, pw = sub[0], sub[1]
+                y = g.dwpw(g.mat(x), packed(dw.conv, dw.bn, dw), act_flag(dw.act), packed(pw.conv, pw.bn, pw),
+                           act_flag(pw.act))
+            x = y if y is not None else emit_any(g, sub, x)
+        return x
 
     def _yl_export(self, g, res):
         y, raws = res
