@@ -16,6 +16,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --inflight 1 --no-cpu-baseline --no-e2e --no-latency --no-roofline > $OUT/ncu_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" -s 240 -c 12 -f -o $OUT/conv_tc \
     python bench.py --steps 1 --warmup 3 --inflight 1 --no-cpu-baseline --no-e2e --no-latency > $OUT/ncu_full.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"c3k2_tail|dwconv3x3_mma|stem_conv|letterbox|nms_|psa_att|sppf" -s 12 -c 16 -f -o $OUT/others \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"c3k2_tail|dwconv3x3_mma|dwpw_tc|stem_|letterbox|nms_|psa_att|sppf" -s 12 -c 16 -f -o $OUT/others \
     python bench.py --steps 1 --warmup 3 --inflight 1 --no-cpu-baseline --no-latency > $OUT/ncu_others.log 2>&1
 ls -la $OUT
