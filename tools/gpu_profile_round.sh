@@ -13,7 +13,7 @@ timeout 120 python tools/layer_times.py n 64 > $OUT/layers_n64.txt 2>&1; tail -1
 timeout 180 python tools/layer_times.py m 64 > $OUT/layers_m64.txt 2>&1; tail -1 $OUT/layers_m64.txt
 timeout 120 python tools/layer_times.py n 1 > $OUT/layers_n1.txt 2>&1; tail -1 $OUT/layers_n1.txt
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 2500 --csv \
-    --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --inflight 1 --no-cpu-baseline --no-e2e --no-latency --no-roofline > $OUT/ncu_bench.log 2>&1
+    --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --inflight 1 --repeats 1 --no-cpu-baseline --no-e2e --no-latency --no-roofline --no-extras > $OUT/ncu_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" -s 240 -c 12 -f -o $OUT/conv_tc \
     python bench.py --steps 1 --warmup 3 --inflight 1 --no-cpu-baseline --no-e2e --no-latency > $OUT/ncu_full.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"c3k2_tail|dwconv3x3_mma|dwpw_tc|stem_|letterbox|nms_|psa_att|sppf" -s 12 -c 16 -f -o $OUT/others \
