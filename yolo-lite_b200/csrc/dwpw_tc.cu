@@ -37,6 +37,7 @@ struct DwPwParams {
     const __nv_bfloat16* dw_w;   // [9][C]
     const float* dw_b;           // [C]
     int C, cblocks, dw_act, raw_stages, a_stages;
+    int dbg_skip;                // timing experiments only (YL_DWPW_SKIP): 1 = depthwise warps skip their math (wrong results)
 };
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -50,8 +51,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // 8-byte store into the swizzled A tile.  `rp`: shared address of patch pixel (first row, column x - 1) + channel offset,
 // `row_bytes` / `pix_bytes`: patch pitches; `ap`: address of the first output row's slot (rows are 16 * 128 B apart).
 template <int R>
-__device__ __forceinline__ void dw_rows(uint32_t rp, uint32_t row_bytes, uint32_t pix_bytes, uint32_t ap, const f32x2 (&w)[9][2],
-                                        const f32x2 (&bia)[2], int act) {
+__device__ __forceinline__ void dw_rows(const uint8_t* rp, uint32_t row_bytes, uint32_t pix_bytes, uint8_t* ap,
+                                        const f32x2 (&w)[9][2], const f32x2 (&bia)[2], int act) {
     // channels (0, 1) and (2, 3) travel as fp32 pairs: one FFMA2 per tap and pair (the loop is instruction-issue bound)
     f32x2 acc[3][2];
 #pragma unroll
@@ -59,11 +60,12 @@ __device__ __forceinline__ void dw_rows(uint32_t rp, uint32_t row_bytes, uint32_
         acc[j][0] = bia[0];
         acc[j][1] = bia[1];
     }
-    // (the loads are volatile asm and the stores carry a memory clobber, so the compiler keeps them in program order: the
-    // next patch row is requested BEFORE the current one is consumed, or every row would expose the shared-memory latency)
+    // (plain loads / stores: the compiler is free to software-pipeline the unrolled rows — hoist the next rows' loads and
+    // FMAs over the SiLU latency of the finished row; the mbarrier waits before and the proxy fence after this function
+    // carry memory clobbers)
     uint2 nxt[3];
 #pragma unroll
-    for (int dc = 0; dc < 3; ++dc) nxt[dc] = lds64(rp + (uint32_t)dc * pix_bytes);
+    for (int dc = 0; dc < 3; ++dc) nxt[dc] = *reinterpret_cast<const uint2*>(rp + dc * pix_bytes);
 #pragma unroll
     for (int pr = 0; pr < R + 2; ++pr) {
         f32x2 xin[3][2];
@@ -75,7 +77,7 @@ __device__ __forceinline__ void dw_rows(uint32_t rp, uint32_t row_bytes, uint32_
         }
         if (pr + 1 < R + 2) {
 #pragma unroll
-            for (int dc = 0; dc < 3; ++dc) nxt[dc] = lds64(rp + (uint32_t)(pr + 1) * row_bytes + (uint32_t)dc * pix_bytes);
+            for (int dc = 0; dc < 3; ++dc) nxt[dc] = *reinterpret_cast<const uint2*>(rp + (pr + 1) * row_bytes + dc * pix_bytes);
         }
 #pragma unroll
         for (int dr = 0; dr < 3; ++dr) {
@@ -98,9 +100,7 @@ __device__ __forceinline__ void dw_rows(uint32_t rp, uint32_t row_bytes, uint32_
 #pragma unroll
                 for (int c = 0; c < 4; ++c) o[c] = silu_fast(o[c]);
             }
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ap + (uint32_t)(rdone * 16 * 128)), "r"(pack_bf16x2(o[0], o[1])),
-                         "r"(pack_bf16x2(o[2], o[3]))
-                         : "memory");
+            *reinterpret_cast<uint2*>(ap + rdone * 16 * 128) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
         }
     }
 }
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_tc_kernel(const __grid_con
                     x = t2 & 15;
                     seg = t2 >> 4;
                 }
-                const bool active = seg < segs;
+                const bool active = seg < segs && !(P.dbg_skip & 1);
                 f32x2 w[9][2], bia[2];
                 if (active) {
 #pragma unroll
@@ -290,9 +290,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_tc_kernel(const __grid_con
                     const int r0 = seg * (kDwTH / segs);                 // first output row of this thread
                     // destination inside a (128 rows x 128 B) SW128 tile: row m = r * 16 + x, 16-byte chunk (cg >> 1) ^ (m & 7)
                     const uint32_t a_col = ((uint32_t)(((cg >> 1) ^ (x & 7)) << 4)) | ((uint32_t)(cg & 1) << 3);
-                    const uint32_t rp = smem_u32(sRaw + (size_t)rs * kDwRawStride) + (uint32_t)r0 * row_bytes +
-                                        (uint32_t)x * pix_bytes + (uint32_t)cg * 8u;
-                    const uint32_t ap = smem_u32(sA + (size_t)as * kDwABytes) + (uint32_t)(r0 * 16 + x) * 128u + a_col;
+                    const uint8_t* rp = sRaw + (size_t)rs * kDwRawStride + (uint32_t)r0 * row_bytes + (uint32_t)x * pix_bytes +
+                                        (uint32_t)cg * 8u;
+                    uint8_t* ap = sA + (size_t)as * kDwABytes + (uint32_t)(r0 * 16 + x) * 128u + a_col;
                     if (segs == 1) dw_rows<8>(rp, row_bytes, pix_bytes, ap, w, bia, P.dw_act);
                     else if (segs == 2) dw_rows<4>(rp, row_bytes, pix_bytes, ap, w, bia, P.dw_act);
                     else dw_rows<2>(rp, row_bytes, pix_bytes, ap, w, bia, P.dw_act);
@@ -434,6 +434,8 @@ int yl_dw_pw_conv(const yl_conv_args* a, const void* dw_w, const float* dw_bias,
     pp->C = x.c;
     pp->cblocks = p.cin_blocks;
     pp->dw_act = dw_act;
+    static const int k_skip = [] { const char* e = getenv("YL_DWPW_SKIP"); return e && *e ? atoi(e) : 0; }();
+    pp->dbg_skip = k_skip;
     pp->raw_stages = raw_stages;
     pp->a_stages = 2;
 
