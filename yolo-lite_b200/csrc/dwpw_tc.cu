@@ -40,12 +40,6 @@ struct DwPwParams {
     int dbg_skip;                // timing experiments only (YL_DWPW_SKIP): 1 = depthwise warps skip their math (wrong results)
 };
 
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-
 // R output rows of one tile column for 4 channels: walks R + 2 patch rows with three rolling accumulators (a patch row is
 // tap row dr of output row pr - dr), finishes an output row as soon as its third patch row has been added: SiLU, bf16,
 // 8-byte store into the swizzled A tile.  `rp`: shared address of patch pixel (first row, column x - 1) + channel offset,
