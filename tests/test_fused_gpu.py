@@ -330,3 +330,40 @@ def test_detect_class_branch_uses_the_fused_dw_pw_kernel():
     kinds = [md["kind"] for md in m._get_plan(x.shape, x.device)[0].meta]
     assert kinds.count("dwpw_tc") == 6, kinds           # 3 levels x 2 stages of the class branch
     assert kinds.count("dwconv3x3") == 2, kinds          # what remains: Attention.pe of C2PSA
+
+
+@pytest.mark.parametrize("c,co,n,h,w,xoff,act_dw,act_pw", [
+    (64, 64, 1, 5, 7, 0, True, True),       # a map smaller than one 16 x 8 tile
+    (64, 80, 2, 9, 33, 16, True, True),     # input is a channel slice (offset 16 of a 96-channel buffer), one column over 2 tiles
+    (32, 48, 70, 8, 16, 0, True, False),    # many images of exactly one tile, no activation on the 1x1
+    (80, 80, 1, 16, 16, 8, False, True),    # no activation on the depthwise conv, sliced 64 + 16 input
+])
+def test_dw_pw_fused_edge_shapes(c, co, n, h, w, xoff, act_dw, act_pw):
+    """Edge shapes of yl_dw_pw_conv against fp32 PyTorch: maps smaller than a tile, channel-slice inputs (TMA base not at
+    the start of a pixel), large batches, either activation switched off."""
+    from yololite import _ops, _plan
+    from yololite._ops import View
+
+    g0 = torch.Generator().manual_seed(1000 + c + co + h)
+    wd = torch.randn(c, 1, 3, 3, generator=g0) * 0.4
+    bd = torch.randn(c, generator=g0) * 0.1
+    wp = torch.randn(co, c, 1, 1, generator=g0) * (1.5 / c ** 0.5)
+    bp = torch.randn(co, generator=g0) * 0.1
+    pdw = _ops.pack_conv(wd, bn=None, conv_bias=bd)
+    ppw = _ops.pack_conv(wp, bn=None, conv_bias=bp)
+    x = torch.rand(n, c, h, w, generator=g0) * 2 - 1
+    buf = torch.full((n, h, w, c + 2 * xoff), 3.25, dtype=torch.bfloat16, device="cuda")
+    buf[..., xoff:xoff + c] = x.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    gb = _plan.Builder(torch.device("cuda", 0))
+    y = gb.dwpw(View(buf, xoff, c), pdw, act_dw, ppw, act_pw)
+    assert y is not None
+    gb.finish().run_eager()
+    torch.cuda.synchronize()
+    got = y.torch_nhwc().float().cpu().permute(0, 3, 1, 2)
+    xr = buf[..., xoff:xoff + c].float().cpu().permute(0, 3, 1, 2)
+    t = F.conv2d(xr, wd.to(torch.bfloat16).float(), bd, 1, 1, 1, c)
+    t = (F.silu(t) if act_dw else t).to(torch.bfloat16).float()
+    ref = F.conv2d(t, wp.to(torch.bfloat16).float(), bp)
+    ref = F.silu(ref) if act_pw else ref
+    assert got.shape == ref.shape
+    assert ((got - ref).abs() <= 4e-2 + 2e-2 * ref.abs()).all(), float((got - ref).abs().max())
