@@ -363,6 +363,18 @@ conv_chain_kernel(const ConvTcParams* __restrict__ layers, int n_layers, uint32_
 }
 
 static int g_chain_max_smem = 0;
+static int g_chain_cluster = 0;   // YL_CHAIN_CLUSTER: 0 = by batch size, else 1 / 2 / 4 / 8 / 16 (read once in yl_init)
+
+// CTAs per image: at tiny batches an image's layer is spread over up to 16 SMs (measured, model graph replay at bs = 1:
+// 0.614 ms with clusters of 4, 0.528 with 8, 0.444 with 16; per-layer launches: 0.343), shrinking to 4 as the batch fills
+// the GPU with one CTA per SM (bs = 16: 0.829 ms with clusters of 8, 1.050 with 16)
+static int chain_cluster_for(int batch) {
+    if (g_chain_cluster == 1 || g_chain_cluster == 2 || g_chain_cluster == 4 || g_chain_cluster == 8 || g_chain_cluster == 16)
+        return g_chain_cluster;
+    int cs = 16;
+    while (cs > 4 && batch * cs > 148) cs >>= 1;
+    return cs;
+}
 static thread_local unsigned long long* g_chain_dbg = nullptr;   // yl_conv_chain_debug: state of the calling thread
 
 int init_conv_chain() {
@@ -370,12 +382,19 @@ int init_conv_chain() {
     YL_CUDA(cudaGetDevice(&dev));
     YL_CUDA(cudaDeviceGetAttribute(&g_chain_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     YL_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_chain_max_smem));
+    // clusters of 16 CTAs (one image spread over 16 SMs at tiny batch sizes) are beyond the portable limit of 8
+    YL_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    {
+        const char* e = getenv("YL_CHAIN_CLUSTER");
+        g_chain_cluster = (e && *e) ? atoi(e) : 0;
+    }
     return YL_OK;
 }
 
-static bool chain_layer_ok(const yl_conv_args* a, ConvTcParams& p, size_t* smem) {
+static bool chain_layer_ok(const yl_conv_args* a, ConvTcParams& p, size_t* smem, int cluster = 0) {
     ConvTcPlanOpts o;
     o.chain = 1;
+    o.chain_cluster = cluster > 0 ? cluster : chain_cluster_for(a->x.n);
     int grid = 0;
     if (plan_conv_tc(a, p, &grid, smem, &o) != YL_OK) return false;
     // the chain kernel instantiates the four bf16-store epilogues on 32-column chunks only
@@ -405,10 +424,11 @@ int yl_conv_chain_build(const yl_conv_args* layers, int n_layers, void* desc_dev
     size_t smem_max = 0;
     uint32_t cols = 32;
     const int batch = layers[0].x.n;
+    const int cluster = yl::chain_cluster_for(batch);
     for (int i = 0; i < n_layers; ++i) {
         size_t smem = 0;
         YL_CHECK(layers[i].x.n == batch, YL_ERR_ARG, "chain layers must share the batch size");
-        if (!yl::chain_layer_ok(&layers[i], host[i], &smem)) {
+        if (!yl::chain_layer_ok(&layers[i], host[i], &smem, cluster)) {
             yl::set_error("layer %d of the chain cannot run in conv_chain_kernel (%d->%d k%d)", i, layers[i].x.c,
                           layers[i].y.c, layers[i].k);
             return YL_ERR_UNSUPPORTED;
@@ -426,7 +446,7 @@ int yl_conv_chain_build(const yl_conv_args* layers, int n_layers, void* desc_dev
     out->desc = desc_dev;
     out->n_layers = n_layers;
     out->batch = batch;
-    out->cluster = 4;
+    out->cluster = cluster;
     out->smem_bytes = (int32_t)smem_total;
     out->tmem_cols = (int32_t)cols;
     out->reserved = 0;

@@ -616,8 +616,9 @@ int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* 
             const int tm = ceil_div(Ho, p.TH) * ceil_div(Wo, p.TW);
             // (1x1 only: every extra N tile of a 3x3 re-reads the nine shifted A boxes, and those layers are bound by
             // L2 -> SM traffic, tools/chain_timeline.py)
-            while (a->k == 1 && tm * n_tiles < 2 * opts->chain_cluster && co16 % (64 * n_tiles) == 0 &&
-                   co16 / (2 * n_tiles) >= 32)
+            // ... unless the cluster is large (tiny batches: the image must be spread over many SMs and L2 is idle)
+            while ((a->k == 1 || opts->chain_cluster > 4) && tm * n_tiles < 2 * opts->chain_cluster &&
+                   co16 % (64 * n_tiles) == 0 && co16 / (2 * n_tiles) >= 32)
                 n_tiles *= 2;
             p.co_tile = ceil_div(ceil_div(co16, n_tiles), 16) * 16;
         }
