@@ -200,6 +200,14 @@ int yl_dwconv3x3(const yl_tensor* x, const yl_tensor* y, const void* w, const fl
  * Needs x.c % 16 == 0, x.c <= 256, y.c <= 128, no residual / upsample / Detect epilogue. */
 int yl_dw_pw_supported(const yl_conv_args* pw);
 int yl_dw_pw_conv(const yl_conv_args* pw, const void* dw_w, const float* dw_bias, int dw_act, void* stream);
+/* Back-to-back form for the LAST stage of the class branch on the engine path: DWConv 3x3 + Conv 1x1 + the head's final
+ * nn.Conv2d(c3, nc, 1) (head.py:48) with its Detect epilogue, in one launch.  The 1x1 result (c3 channels) is not written:
+ * the epilogue rounds it to bf16 into swizzled shared-memory tiles that are the A operand of a SECOND tcgen05 GEMM with the
+ * head conv's weights, whose accumulator feeds the class decode / class filter.  `head`: the yl_conv_args of the final conv
+ * with det.mode = YL_DET_CLS or YL_DET_CLS_FILTER and y.data == NULL (its x is ignored); head->x.c == pw->y.c <= 128,
+ * nc <= 128.  Bit-identical to yl_dw_pw_conv followed by yl_conv_bn_act(head). */
+int yl_dw_pw_det_supported(const yl_conv_args* pw, const yl_conv_args* head);
+int yl_dw_pw_det(const yl_conv_args* pw, const void* dw_w, const float* dw_bias, int dw_act, const yl_conv_args* head, void* stream);
 
 /* SPPF's three chained MaxPool2d(5,1,2) (block.py:182-184), -inf padding; y1=m(x), y2=m(y1), y3=m(y2). */
 int yl_sppf_pool(const yl_tensor* x, const yl_tensor* y1, const yl_tensor* y2, const yl_tensor* y3, int k,

@@ -367,3 +367,36 @@ def test_dw_pw_fused_edge_shapes(c, co, n, h, w, xoff, act_dw, act_pw):
     ref = F.silu(ref) if act_pw else ref
     assert got.shape == ref.shape
     assert ((got - ref).abs() <= 4e-2 + 2e-2 * ref.abs()).all(), float((got - ref).abs().max())
+
+
+def test_back_to_back_class_tail_equals_the_two_launches(monkeypatch):
+    """yl_dw_pw_det (DWConv + Conv + final class conv with its Detect epilogue as two back-to-back GEMMs in one launch)
+    against yl_dw_pw_conv followed by the head conv: the prediction of `infer` (class decode) and the detections of
+    `infer_nms` (class filter) must be bit-identical, also at a confidence low enough that every anchor is a candidate."""
+    from bench import randomise_model_
+    from yololite.nn.tasks import DetectionModel
+
+    x = torch.rand(3, 3, 320, 448, generator=torch.Generator().manual_seed(21)).cuda()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("YL_DWPW_DET", mode)
+        torch.manual_seed(7)
+        m = randomise_model_(DetectionModel("yolo11n.yaml", verbose=False)).eval().cuda()
+        y, _ = m.infer(x)
+        torch.cuda.synchronize()
+        out = [y.clone()]
+        for conf in (0.001, 0.25):
+            d, c = m.infer_nms(x, conf=conf, iou=0.7)
+            torch.cuda.synchronize()
+            out += [d.clone(), c.clone()]
+        d, c = m.infer_nms(x, conf=0.25, iou=0.7)          # replay of the captured plan
+        torch.cuda.synchronize()
+        out += [d.clone(), c.clone()]
+        res[mode] = out
+        descs = [md["desc"] for md in m._get_plan(x.shape, x.device)[0].meta if md["kind"] in ("conv_tc", "dwpw_tc")]
+        fused_tail = [d for d in descs if d.startswith("[dw3x3") and "+decode]" in d]
+        plain_cls = [d for d in descs if "->80 k1s1" in d and d.endswith("+decode") and d.startswith("80->")]
+        assert (len(fused_tail), len(plain_cls)) == ((3, 0) if mode == "1" else (0, 3)), descs[-12:]
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.equal(a, b), float((a.float() - b.float()).abs().max())
+    assert int(res["1"][2].sum()) > 0 and int(res["1"][4].sum()) > 0

@@ -138,6 +138,8 @@ _PROTOTYPES = {
                                C.POINTER(Tensor), C.c_void_p]),
     "yl_dw_pw_supported": (C.c_int, [C.POINTER(ConvArgs)]),
     "yl_dw_pw_conv": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "yl_dw_pw_det_supported": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvArgs)]),
+    "yl_dw_pw_det": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ConvArgs), C.c_void_p]),
     "yl_sppf_pool": (C.c_int, [C.POINTER(Tensor)] * 4 + [C.c_int, C.c_void_p]),
     "yl_psa_attention": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_void_p]),

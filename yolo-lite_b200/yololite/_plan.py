@@ -83,6 +83,7 @@ class Builder:
         self.chain_max_hw = int(os.environ.get("YL_CHAIN_MAX_HW", "1600"))
         # DWConv 3x3 + Conv 1x1 pairs (Detect class branch) as one launch (csrc/dwpw_tc.cu)
         self.dwpw_enabled = os.environ.get("YL_DWPW", "1") != "0"
+        self.dwpw_det_enabled = os.environ.get("YL_DWPW_DET", "1") != "0"
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -246,6 +247,33 @@ class Builder:
                    flops=2 * px * (9 * x.c + x.c * ppw.co), desc=f"[dw3x3 {x.c}, {x.c}->{ppw.co} k1] {x.h}x{x.w}",
                    reads=(x,), writes=(y,))
         return y
+
+    def dwpw_det(self, x: View, pdw: PackedConv, act_dw: bool, ppw: PackedConv, act_pw: bool, plast: PackedConv, det) -> bool:
+        """Last stage of a Detect class branch on the engine path: DWConv 3x3 + Conv 1x1 + the final 1x1 conv with its
+        Detect epilogue (class decode / class filter, no NHWC store) as ONE launch (yl_dw_pw_det: two back-to-back tcgen05
+        GEMMs, the c3-channel tensor between them stays in shared memory).  False when the kernel does not take the shape."""
+        x = self.mat(x)
+        if not (self.dwpw_enabled and self.dwpw_det_enabled and pdw.depthwise and pdw.k == 3 and ppw.k == 1 and plast.k == 1
+                and not ppw.depthwise and not plast.depthwise and pdw.co == x.c and pdw.co_pad == x.c and ppw.ci == x.c
+                and plast.ci == ppw.co):
+            return False
+        mid = _ops.NoOutput(x.n, x.h, x.w, ppw.co, torch.bfloat16)
+        a1 = _ops.conv_args(x, mid, ppw, 1, act_pw, None, False, _C.IMPL_TCGEN05, None, None)
+        a2 = _ops.conv_args(mid, _ops.NoOutput(x.n, x.h, x.w, plast.co, torch.float32), plast, 1, False, None, False,
+                            _C.IMPL_TCGEN05, None, det)
+        if not self.lib.yl_dw_pw_det_supported(C.byref(a1), C.byref(a2)):
+            return False
+        px = x.n * x.h * x.w
+        filt = det.mode == _C.DET_CLS_FILTER
+        self._push(self.lib.yl_dw_pw_det, C.byref(a1), pdw.w.data_ptr(), pdw.bias.data_ptr(), int(bool(act_dw)), C.byref(a2),
+                   keep=(a1, a2, pdw, ppw, plast, det), kind="dwpw_tc",
+                   bytes_=px * x.c * 2 + (0 if filt else px * det.nc * 4) + (9 * x.c + x.c * ppw.co + ppw.co * plast.co) * 2,
+                   flops=2 * px * (9 * x.c + x.c * ppw.co + ppw.co * plast.co),
+                   desc=f"[dw3x3 {x.c}, {x.c}->{ppw.co} k1, {ppw.co}->{plast.co} k1 {'+filter' if filt else '+decode'}] {x.h}x{x.w}",
+                   reads=(x,),
+                   writes=((det.cand_ws, 1 + det.anchor0, 2 + det.anchor0) if filt else
+                           (det.pred, 2 * det.anchor0 + 1, 2 * det.anchor0 + 2),))
+        return True
 
     def stem_fused(self, x: NchwInput, pc0: PackedConv, pc1: PackedConv, act0: bool, act1: bool, out=None) -> View:
         """Image ingest + the first two stride-2 3x3 convs in one launch (see yl_stem_fused)."""
@@ -525,7 +553,7 @@ class Plan:
         times = []
         # the one exception to idempotence: head convs with the fused class filter APPEND candidates (atomic counters
         # zeroed by yl_nms_begin); they are issued once per pass so the select kernel sees each candidate once
-        once = [" +filter" in md["desc"] for md in self.meta]
+        once = ["+filter" in md["desc"] for md in self.meta]
         for _ in range(reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n)]
             for i, (fn, args, _) in enumerate(self.calls):

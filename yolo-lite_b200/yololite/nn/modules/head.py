@@ -114,13 +114,17 @@ class Detect(YLModule):
                 # them next to the rest of the neck (the last level's box branch stays on the main lane)
                 lane = 0 if (i == self.nl - 1 and j == 0) or not self.parallel_branches else 1 + 2 * i + j
                 with g.lane(lane):
-                    t = self._emit_branch(g, branch[:-1], x)
                     last = branch[-1]
                     if filt and mode == _C.DET_CLS:
                         det = _ops.DetEpilogue(y, _C.DET_CLS_FILTER, self.reg_max, self.nc, a0, float(self.stride[i]),
                                                conf=conf, cand_ws=cand_ws)
                     else:
                         det = _ops.DetEpilogue(y, mode, self.reg_max, self.nc, a0, float(self.stride[i]))
+                    # engine path, class branch: its last stage (DWConv + Conv) and the final conv + Detect epilogue run as
+                    # one back-to-back launch when the kernel takes the shape
+                    if mode == _C.DET_CLS and not want_raw and self._emit_cls_tail(g, branch, x, det):
+                        continue
+                    t = self._emit_branch(g, branch[:-1], x)
                     g.conv(t, packed(last, None, last), 1, act=False, out=raw.slice(lo, cnt) if want_raw else None,
                            out_dtype=torch.float32, det=det, store=want_raw)
             if want_raw:
@@ -144,6 +148,30 @@ class Detect(YLModule):
                            act_flag(pw.act))
             x = y if y is not None else emit_any(g, sub, x)
         return x
+
+    @classmethod
+    def _emit_cls_tail(cls, g, branch, x, det) -> bool:
+        """[..., Sequential(DWConv 3x3, Conv 1x1), Conv2d 1x1 + Detect epilogue] with the last two as ONE launch
+        (yl_dw_pw_det).  Emits the earlier stages and returns True, or emits nothing and returns False."""
+        from ._emit import act_flag, packed
+
+        if len(branch) < 2 or not isinstance(branch[-1], nn.Conv2d):
+            return False
+        sub, last = branch[-2], branch[-1]
+        if not (isinstance(sub, nn.Sequential) and len(sub) == 2 and isinstance(sub[0], DWConv) and type(sub[1]) is Conv
+                and sub[0].conv.kernel_size == (3, 3) and sub[0].conv.stride == (1, 1)
+                and sub[1].conv.kernel_size == (1, 1) and sub[1].conv.stride == (1, 1) and sub[1].conv.groups == 1
+                and last.kernel_size == (1, 1) and last.stride == (1, 1) and last.groups == 1):
+            return False
+        t = cls._emit_branch(g, branch[:-2], x)
+        dw, pw = sub[0], sub[1]
+        if g.dwpw_det(g.mat(t), packed(dw.conv, dw.bn, dw), act_flag(dw.act), packed(pw.conv, pw.bn, pw), act_flag(pw.act),
+                      packed(last, None, last), det):
+            return True
+        # the back-to-back kernel does not take the shape: finish the branch the plain way
+        t = cls._emit_branch(g, branch[-2:-1], t)
+        g.conv(t, packed(last, None, last), 1, act=False, out=None, out_dtype=torch.float32, det=det, store=False)
+        return True
 
     def _yl_export(self, g, res):
         y, raws = res
