@@ -143,3 +143,58 @@ def test_plan_dependency_tracking_on_channel_slices():
     assert b._track(3, (View(buf, 0, 16),), ()) == (0,)                # reads only the first producer's slice
     assert b._track(4, (View(other, 0, 16),), (View(buf, 0, 64),)) == (0, 1, 2, 3)  # overwrite: WAW + WAR
     assert b._track(5, (View(buf, 40, 8),), ()) == (1, 4)              # every overlapping earlier writer
+
+
+def test_conv_chain_grouping_and_dependency_remap():
+    """Builder._fuse_chains (host logic only, stub library): runs of consecutive chainable convs of ONE lane become one
+    call; a run is broken by any other launch and by a lane change; the chain inherits its members' outside dependencies
+    and later calls' dependencies are renumbered onto it."""
+    import ctypes as C
+    import types
+
+    import torch
+
+    from yololite import _C, _plan
+
+    built = []
+
+    def build(arr, n, ptr, nbytes, out, stream):
+        built.append(n)
+        return 0
+
+    # (a ctypes library hands out ONE function object per symbol; the plan compares them by identity)
+    lib = types.SimpleNamespace(yl_conv_bn_act=lambda *a: 0, yl_other=lambda *a: 0, yl_conv_chain_supported=lambda a: 1,
+                                yl_conv_chain_desc_bytes=lambda n: 64 * n, yl_conv_chain_build=build,
+                                yl_conv_chain_run=lambda *a: 0)
+    b = _plan.Builder.__new__(_plan.Builder)
+    b.lib, b.device, b.buffers = lib, torch.device("cpu"), []
+    b.chain_enabled, b.chain_min_batch, b.chain_max_hw = True, 1, 1600
+
+    def conv_call(hw=20, n=4):
+        a = _C.ConvArgs()
+        a.x.n, a.x.h, a.x.w, a.y.h, a.y.w = n, hw, hw, hw, hw
+        return (lib.yl_conv_bn_act, (C.byref(a),), (a, None, None)), {"kind": "conv_tc", "bytes": 10, "flops": 100, "desc": f"c{hw}"}
+
+    other = ((lib.yl_other, (), ()), {"kind": "pool", "bytes": 1, "flops": 0, "desc": "pool"})
+    seq = [conv_call(80), conv_call(), conv_call(), conv_call(), other, conv_call(), conv_call(), conv_call(), conv_call()]
+    b.calls = [c for c, _ in seq]
+    b.meta = [m for _, m in seq]
+    b.lanes = [0, 0, 0, 0, 0, 0, 0, 1, 1]
+    #            0    1     2     3       4     5     6     7       8
+    b.deps = [(), (0,), (1,), (1, 2), (3,), (4,), (5,), (4, 6), (7,)]
+    import yololite._C as cmod
+
+    orig = cmod.stream_ptr
+    cmod.stream_ptr = lambda *a, **k: 0
+    try:
+        b._fuse_chains()
+    finally:
+        cmod.stream_ptr = orig
+    kinds = [m["kind"] for m in b.meta]
+    # call 0 (80x80: too large) stays; 1-3 chain; pool; 5-6 chain (lane 0); 7-8 chain (lane 1)
+    assert kinds == ["conv_tc", "conv_chain", "pool", "conv_chain", "conv_chain"], kinds
+    assert built == [3, 2, 2]
+    assert b.lanes == [0, 0, 0, 0, 1]
+    assert b.deps == [(), (0,), (1,), (2,), (2, 3)], b.deps
+    assert [len(m.get("members", [])) for m in b.meta] == [0, 3, 0, 2, 2]
+    assert b.meta[1]["bytes"] == 30 and b.meta[1]["flops"] == 300
