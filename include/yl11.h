@@ -141,6 +141,14 @@ typedef struct yl_conv_args {
     yl_det_epilogue det;    /* det.pred == NULL: none (tcgen05 path only, k = 1, stride 1, no act/res) */
 } yl_conv_args;
 int yl_conv_bn_act(const yl_conv_args* a, void* stream);
+/* Back-to-back form for the tail of a Detect BOX branch on the engine path (head.py:39-41, 59-65): the branch's last
+ * Conv(c2, c2, 3) and the final nn.Conv2d(c2, 4 * reg_max, 1) with its DFL / dist2bbox decode in ONE launch.  `conv` is the
+ * 3x3 conv (k in {1,3}, y.data == NULL: its result is not stored, y gives dims / channels <= 128); its epilogue rounds the
+ * result to bf16 into swizzled shared-memory tiles that are the A operand of a second tcgen05 GEMM with `head`'s weights
+ * (head: 1x1, no activation, y.data == NULL, det.mode = YL_DET_BOX or YL_DET_CLS, its x is ignored).  Bit-identical to
+ * yl_conv_bn_act(conv) followed by yl_conv_bn_act(head). */
+int yl_conv_b2b_det_supported(const yl_conv_args* conv, const yl_conv_args* head);
+int yl_conv_b2b_det(const yl_conv_args* conv, const yl_conv_args* head, void* stream);
 /* 1 if the tcgen05 implicit-GEMM path can run this problem, 0 if it needs the direct kernel. */
 int yl_conv_tc_supported(const yl_conv_args* a);
 /* How the tcgen05 path would run this problem (the host-side dispatch of conv_tc.cu; nothing is launched): tests

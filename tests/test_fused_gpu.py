@@ -400,3 +400,38 @@ def test_back_to_back_class_tail_equals_the_two_launches(monkeypatch):
     for a, b in zip(res["0"], res["1"]):
         assert torch.equal(a, b), float((a.float() - b.float()).abs().max())
     assert int(res["1"][2].sum()) > 0 and int(res["1"][4].sum()) > 0
+
+
+def test_back_to_back_box_tail_equals_the_two_launches(monkeypatch):
+    """yl_conv_b2b_det (last 3x3 conv of the Detect box branch + the final 1x1 conv + DFL / dist2bbox decode as two
+    back-to-back GEMMs in one launch of the conv_tc back-to-back instantiation) against the two launches: `infer` and
+    `infer_nms` must be bit-identical; covers the halo-patch (80x80, 40x40 maps) and the streamed-tap (small map) modes."""
+    from bench import randomise_model_
+    from yololite.nn.tasks import DetectionModel
+
+    x = torch.rand(2, 3, 640, 640, generator=torch.Generator().manual_seed(23)).cuda()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("YL_CONV_DET", mode)
+        torch.manual_seed(7)
+        m = randomise_model_(DetectionModel("yolo11n.yaml", verbose=False)).eval().cuda()
+        y, _ = m.infer(x)
+        torch.cuda.synchronize()
+        out = [y.clone()]
+        d, c = m.infer_nms(x, conf=0.25, iou=0.7)
+        torch.cuda.synchronize()
+        out += [d.clone(), c.clone()]
+        y2, _ = m.infer(x)                                   # replay
+        torch.cuda.synchronize()
+        out += [y2.clone()]
+        res[mode] = out
+        descs = [md["desc"] for md in m._get_plan(x.shape, x.device)[0].meta if md["kind"] == "conv_tc"]
+        fused = [d for d in descs if d.startswith("[64->64 k3s1, 64->64 k1 +decode]")]
+        plain = [d for d in descs if d.startswith("64->64 k1s1") and d.endswith("+decode")]
+        # (at this small batch the 20x20 level takes the small-problem N split, which the back-to-back kernel does not
+        # support: that level falls back to the two launches)
+        assert len(fused) + len(plain) == 3 and (len(fused) >= 2 if mode == "1" else len(fused) == 0), descs[-12:]
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.equal(a, b), float((a.float() - b.float()).abs().max())
+    assert torch.equal(res["1"][0], res["1"][3])
+    assert int(res["1"][2].sum()) > 0

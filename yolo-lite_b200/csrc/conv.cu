@@ -8,6 +8,8 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len);
 int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream);
 int launch_conv_direct(const yl_conv_args* a, cudaStream_t stream);
 int conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out);
+int launch_conv_b2b(const yl_conv_args* a, const yl_conv_args* head, cudaStream_t stream);
+bool conv_b2b_supported(const yl_conv_args* a, const yl_conv_args* head);
 }  // namespace yl
 
 extern "C" {
@@ -20,6 +22,16 @@ int yl_conv_tc_supported(const yl_conv_args* a) {
 int yl_conv_tc_info(const yl_conv_args* a, yl_conv_tc_plan* out) {
     YL_CHECK(a != nullptr && out != nullptr, YL_ERR_ARG, "null argument");
     return yl::conv_tc_info(a, out);
+}
+
+int yl_conv_b2b_det_supported(const yl_conv_args* conv, const yl_conv_args* head) {
+    return conv && head && yl::conv_b2b_supported(conv, head) ? 1 : 0;
+}
+
+int yl_conv_b2b_det(const yl_conv_args* conv, const yl_conv_args* head, void* stream) {
+    YL_CHECK(conv && head && conv->x.data && conv->w && conv->bias && head->w && head->bias && head->det.pred, YL_ERR_ARG,
+             "null pointer");
+    return yl::launch_conv_b2b(conv, head, (cudaStream_t)stream);
 }
 
 int yl_conv_bn_act(const yl_conv_args* a, void* stream) {

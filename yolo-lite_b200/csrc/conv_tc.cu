@@ -35,7 +35,9 @@ namespace yl {
 // Persistent: gridDim.x CTAs each walk tiles blockIdx.x, +gridDim.x, ...  The TMA producer runs ahead across
 // tile boundaries (the smem ring never drains), and with two TMEM accumulator stages the epilogue of tile i
 // overlaps the loads and MMAs of tiles i+1, i+2.
-template <bool DBG>
+// B2B = true: the back-to-back instantiation (a second 1x1 GEMM + Detect decode behind the conv, see conv_tc.cuh); a
+// separate instantiation so that the production kernel's code and register allocation stay exactly what they were.
+template <bool DBG, bool B2B = false>
 __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // broadcast from lane 0 so the compiler treats the warp index (and every role / tile index derived from it)
@@ -57,6 +59,20 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
     uint64_t* w_bar = tempty_bar + 2;             // patch mode: resident weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    // back-to-back mode: second GEMM's weight tiles, bias and barriers live behind everything else
+    uint8_t* sB3 = nullptr;
+    float* sbias3 = nullptr;
+    uint64_t *a2_full = nullptr, *a2_empty = nullptr, *tfull2_bar = nullptr, *tempty2_bar = nullptr, *w3_bar = nullptr;
+    if constexpr (B2B) {
+        const uint32_t t = smem_u32(tmem_slot + 1);
+        sB3 = reinterpret_cast<uint8_t*>(tmem_slot + 1) + (((t + 1023u) & ~1023u) - t);
+        sbias3 = reinterpret_cast<float*>(sB3 + (size_t)p.k2blocks * p.b3_bytes);
+        a2_full = reinterpret_cast<uint64_t*>(sbias3 + ((p.co_tile3 + 32 + 3) & ~3));
+        a2_empty = a2_full + 2;
+        tfull2_bar = a2_empty + 2;
+        tempty2_bar = tfull2_bar + 2;
+        w3_bar = tempty2_bar + 2;
+    }
 
     // programmatic dependent launch: let the next kernel of the stream start its prologue as our CTAs retire
     griddep_launch_dependents();
@@ -71,6 +87,15 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
             mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp of the group
         }
         mbar_init(w_bar, 1);
+        if constexpr (B2B) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&a2_full[s], 1);
+                mbar_init(&a2_empty[s], 1);
+                mbar_init(&tfull2_bar[s], 1);
+                mbar_init(&tempty2_bar[s], 4);
+            }
+            mbar_init(w3_bar, 1);
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -85,6 +110,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     {
         const float bs = p.act ? 0.5f : 1.0f;   // activated convs stage b / 2 (the epilogue works on h = x / 2)
         for (int i = threadIdx.x; i < nbias; i += blockDim.x) sbias[i] = i < p.n_bias ? bs * __ldg(p.bias + i) : 0.f;
+        if constexpr (B2B)
+            for (int i = threadIdx.x; i < p.co_tile3 + 32; i += blockDim.x) sbias3[i] = i < p.n_bias3 ? __ldg(p.bias3 + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -93,6 +120,13 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
     if (threadIdx.x == 0) YL_STAMP(1);
     const int taps = p.ksize * p.ksize;
     const int kiters = taps * p.cin_blocks;
+    if constexpr (B2B) {
+        // the second GEMM's weights are constants: fetched before the dependency wait
+        if (warp == 0 && elect_one()) {
+            mbar_expect_tx(w3_bar, (uint32_t)p.k2blocks * (uint32_t)p.co_tile3 * 128u);
+            for (int kb = 0; kb < p.k2blocks; ++kb) tma_load_2d(sB3 + (size_t)kb * p.b3_bytes, &p.tmB3, w3_bar, kb * 64, 0);
+        }
+    }
     // resident weights are constants too: their TMA loads are issued before the dependency wait, so they fly
     // while the previous kernel of the stream is still draining
     if (warp == 0 && p.wearly && (p.patch || p.wres) && elect_one()) {
@@ -199,6 +233,33 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
             mbar_wait(w_bar, 0);
             tc_fence_after();
         }
+        // back-to-back: D2[g] = A2[g] (this CTA's j-th tile, written by epilogue group g = j & 1) x W3^T, issued one tile
+        // behind the first GEMM so that neither waits for the other's epilogue
+        int ntile = 0;
+        auto mma2 = [&](int j) {
+            const int g2 = j & 1;
+            const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+            mbar_wait(&a2_full[g2], ph2);
+            mbar_wait(&tempty2_bar[g2], ph2 ^ 1u);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)p.co_tile3);
+                const uint32_t d2 = tmem_base + (uint32_t)(2 * p.acc_stride + g2 * p.acc3_stride);
+                for (int kb = 0; kb < p.k2blocks; ++kb) {
+                    const int ks2 = (min(64, p.c2_ch - kb * 64) + 15) >> 4;
+                    const uint64_t da2 = umma_desc_kmajor(smem_u32(sStg + (size_t)g2 * p.stg_bufs * p.stg_bytes + (size_t)kb * 16384), 128u);
+                    const uint64_t db2 = umma_desc_kmajor(smem_u32(sB3 + (size_t)kb * p.b3_bytes), 128u);
+                    for (int k = 0; k < ks2; ++k)
+                        umma_bf16(d2, da2 + (uint64_t)(2 * k), db2 + (uint64_t)(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&a2_empty[g2]);
+                umma_commit(&tfull2_bar[g2]);
+            }
+        };
+        if constexpr (B2B) {
+            mbar_wait(w3_bar, 0);
+            tc_fence_after();
+        }
         if (p.patch) {
             const uint32_t sbo = (uint32_t)p.patch_pw * rb;       // next 8-row group = next patch row (TW == 8)
             const uint32_t wtap = (uint32_t)p.co_tile * rb;       // bytes of one tap's weight tile
@@ -235,6 +296,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
                 }
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1u;
+                if constexpr (B2B) {
+                    if (ntile > 0) mma2(ntile - 1);
+                    ++ntile;
+                }
             }
         } else {
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -263,7 +328,14 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
                 if (leader) umma_commit(&tfull_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1u;
+                if constexpr (B2B) {
+                    if (ntile > 0) mma2(ntile - 1);
+                    ++ntile;
+                }
             }
+        }
+        if constexpr (B2B) {
+            if (ntile > 0) mma2(ntile - 1);
         }
     } else {
         // ================= epilogue =================
@@ -283,6 +355,15 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
 #define YL_EPI(CW_, ACT_, RES_, DET_, GEN_) \
     conv_tc_epilogue<CW_, ACT_, RES_, DET_, GEN_, DBG>(p, p, tr, acc_uses, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, \
                                                        stg, sbias)
+        if constexpr (B2B) {
+            uint8_t* a2 = sStg + (size_t)g * p.stg_bufs * p.stg_bytes;
+            if (p.act)
+                conv_tc_epilogue_b2b<true>(p, tr, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, a2_full, a2_empty,
+                                           tfull2_bar, tempty2_bar, a2, sbias, sbias3);
+            else
+                conv_tc_epilogue_b2b<false>(p, tr, g, q, lane, gtid, tmem_base, tfull_bar, tempty_bar, a2_full, a2_empty,
+                                            tfull2_bar, tempty2_bar, a2, sbias, sbias3);
+        } else {
         const int kind = DBG ? 7 : p.epi_kind;     // the timeline build keeps only the generic code
         if (kind == 0) YL_EPI(32, true, false, 0, false);
         else if (kind == 1) YL_EPI(32, true, true, 0, false);
@@ -293,6 +374,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 2) conv_tc_kernel(const __grid
         else if (kind == 6) YL_EPI(32, false, false, YL_DET_CLS_FILTER, false);
         else if (p.cw == 32) YL_EPI(32, false, false, 0, true);
         else YL_EPI(16, false, false, 0, true);
+        }
 #undef YL_EPI
     }
 
@@ -322,6 +404,7 @@ int init_conv_tc() {
     YL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     YL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     YL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    YL_CUDA((cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin)));
     return YL_OK;
 }
 
@@ -375,7 +458,11 @@ static void choose_patch(int Ho, int Wo, int N, int* TH, int* TW, int* TN) {
     *TN = bn;
 }
 
+static bool conv_tc_supported_ex(const yl_conv_args* a, char* why, size_t why_len, bool allow_no_output);
 bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
+    return conv_tc_supported_ex(a, why, why_len, false);
+}
+static bool conv_tc_supported_ex(const yl_conv_args* a, char* why, size_t why_len, bool allow_no_output) {
 #define NOPE(msg)                                   \
     do {                                            \
         if (why) snprintf(why, why_len, "%s", msg); \
@@ -415,7 +502,7 @@ bool conv_tc_supported(const yl_conv_args* a, char* why, size_t why_len) {
             NOPE("bad Detect-decode mode");
         }
         if (d.nc < 1 || d.A < 1 || d.anchor0 < 0 || d.anchor0 + x.h * x.w > d.A) NOPE("bad Detect-decode anchor range");
-    } else if (!y.data) {
+    } else if (!y.data && !allow_no_output) {
         NOPE("null output");
     }
     return true;
@@ -488,7 +575,23 @@ static void read_knobs() {
 // smem carve-up and the tensor maps.  Shared by the launch and by yl_conv_tc_info (tests assert which path ran).
 int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* smem_out, const ConvTcPlanOpts* opts) {
     char why[128];
-    YL_CHECK(conv_tc_supported(a, why, sizeof(why)), YL_ERR_UNSUPPORTED, "tcgen05 conv unsupported: %s", why);
+    const yl_conv_args* head = opts ? opts->head : nullptr;
+    YL_CHECK(conv_tc_supported_ex(a, why, sizeof(why), head != nullptr), YL_ERR_UNSUPPORTED, "tcgen05 conv unsupported: %s", why);
+    if (head) {
+        const yl_det_epilogue& d = head->det;
+        YL_CHECK(!a->det.pred && !a->y.data && !a->res.data && !a->y_up.data && !a->upsample2x && a->y.dtype == YL_BF16,
+                 YL_ERR_UNSUPPORTED, "back-to-back: the first conv is a plain bf16 conv whose result is not stored");
+        YL_CHECK(head->k == 1 && head->stride == 1 && !head->act && !head->res.data && !head->y_up.data && !head->upsample2x &&
+                     !head->y.data && d.pred && (d.mode == YL_DET_BOX || d.mode == YL_DET_CLS),
+                 YL_ERR_UNSUPPORTED, "back-to-back: the head conv is a plain 1x1 with a box / class decode epilogue, not stored");
+        YL_CHECK(head->x.c == a->y.c && a->y.c <= 128 && head->y.c <= 128 && head->y.c % 8 == 0 && head->ci_pad >= head->x.c &&
+                     head->ci_pad % 8 == 0 && head->co_pad >= head->y.c && head->co_pad % 8 == 0,
+                 YL_ERR_UNSUPPORTED, "back-to-back: channel counts (<= 128, head input = conv output)");
+        YL_CHECK(d.mode == YL_DET_BOX ? (d.reg_max == 16 && head->y.c == 64) : (head->y.c == d.nc), YL_ERR_UNSUPPORTED,
+                 "back-to-back: box decode needs reg_max 16 (64 channels), class decode co == nc");
+        YL_CHECK(d.nc >= 1 && d.A >= 1 && d.anchor0 >= 0, YL_ERR_ARG, "bad Detect-decode anchor range");
+        YL_CHECK((((uintptr_t)head->w | (uintptr_t)head->bias) & 15) == 0, YL_ERR_ARG, "pointers must be 16-byte aligned");
+    }
     const yl_tensor& x = a->x;
     const yl_tensor& y = a->y;
     const int pad = a->k / 2;
@@ -696,6 +799,24 @@ int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* 
     uint32_t cols = 32;
     while ((int)cols < 2 * p.acc_stride) cols <<= 1;
     YL_CHECK(cols <= 512, YL_ERR_UNSUPPORTED, "accumulator needs %u TMEM columns", cols);
+    if (head) {
+        YL_CHECK(n_tiles == 1 && p.cw == 32, YL_ERR_UNSUPPORTED, "back-to-back needs one N tile of 32-column chunks");
+        p.b2b = 1;
+        p.c2_ch = y.c;
+        p.k2blocks = ceil_div(p.co_tile, 64);
+        p.co_tile3 = ceil_div(head->y.c, 16) * 16;
+        p.nchunks3 = ceil_div(p.co_tile3, 32);
+        p.acc3_stride = p.nchunks3 * 32;
+        p.b3_bytes = ((uint32_t)p.co_tile3 * 128u + 1023u) & ~1023u;
+        p.bias3 = head->bias;
+        p.n_bias3 = head->co_pad;
+        while ((int)cols < 2 * p.acc_stride + 2 * p.acc3_stride) cols <<= 1;
+        YL_CHECK(cols <= 512, YL_ERR_UNSUPPORTED, "back-to-back accumulators need %u TMEM columns", cols);
+        uint64_t dims[2] = {(uint64_t)head->ci_pad, (uint64_t)head->co_pad};
+        uint64_t str[1] = {(uint64_t)head->ci_pad * 2};
+        uint32_t box[2] = {64u, (uint32_t)p.co_tile3};
+        if (!encode_map(&p.tmB3, bf, const_cast<void*>(head->w), 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return YL_ERR_CUDA;
+    }
     p.tmem_cols = cols;
     int ctas_per_sm = (cols <= 256) ? 2 : 1;
     if (chain) YL_CHECK(cols <= 256, YL_ERR_UNSUPPORTED, "chain layer needs %u TMEM columns (two CTAs share an SM)", cols);
@@ -730,6 +851,11 @@ int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* 
         p.stg_row_bytes = p.stg_sub * p.cw * oes;
         p.stg_bytes = (128u * (uint32_t)p.stg_row_bytes + 1023u) & ~1023u;  // 128 rows; 1024-B swizzle atoms
         fixed = 1024 + 2 * (size_t)p.stg_bufs * p.stg_bytes + (size_t)((nbias + 3) & ~3) * 4 + 16;
+        if (head) {
+            // the staging tiles double as the second GEMM's A tiles: a group needs k2blocks tiles of 128 rows x 128 B
+            if ((size_t)p.stg_bufs * p.stg_bytes < (size_t)p.k2blocks * 16384) continue;
+            fixed += 1024 + (size_t)p.k2blocks * p.b3_bytes + (size_t)((p.co_tile3 + 32 + 3) & ~3) * 4 + 9 * 8 + 64;
+        }
         const long long budget = (long long)cta_smem - (long long)fixed - (long long)fixed_b - 16 * 24 - 64;
         if (chain) {
             // two rings: activations (ring A: one stage per k-iteration, or per (tile, channel block) patch) and weights
@@ -772,6 +898,9 @@ int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* 
     }
     p.nstore = ceil_div(p.nchunks, p.stg_sub);
     if (chain) YL_CHECK(stages > 0, YL_ERR_UNSUPPORTED, "chain layer does not fit the shared-memory budget");
+    if (head)
+        YL_CHECK((size_t)p.stg_bufs * p.stg_bytes >= (size_t)p.k2blocks * 16384, YL_ERR_UNSUPPORTED,
+                 "back-to-back: no shared memory left for the second GEMM's A tiles");
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -801,6 +930,18 @@ int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* 
     }
 
     p.store_y = y.data != nullptr;
+    if (head) {
+        p.det_mode = head->det.mode;
+        p.det_pred = head->det.pred;
+        p.det_nc = head->det.nc;
+        p.det_A = head->det.A;
+        p.det_anchor0 = head->det.anchor0;
+        p.det_hw = Ho * Wo;
+        p.det_w = Wo;
+        p.det_stride = head->det.stride;
+        p.det_M = (long long)x.n * Ho * Wo;
+        YL_CHECK(head->det.anchor0 + Ho * Wo <= head->det.A, YL_ERR_ARG, "bad Detect-decode anchor range");
+    }
     if (a->det.pred) {
         p.det_mode = a->det.mode;
         p.det_pred = a->det.pred;
@@ -837,6 +978,28 @@ int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* 
     *grid_out = grid;
     *smem_out = smem;
     return YL_OK;
+}
+
+int launch_conv_b2b(const yl_conv_args* a, const yl_conv_args* head, cudaStream_t stream) {
+    ConvTcParams p;
+    int grid = 0;
+    size_t smem = 0;
+    ConvTcPlanOpts o;
+    o.head = head;
+    const int rc = plan_conv_tc(a, p, &grid, &smem, &o);
+    if (rc != YL_OK) return rc;
+    YL_CUDA(launch_kernel(conv_tc_kernel<false, true>, dim3(grid), dim3(kConvTcThreads), smem, stream, p));
+    YL_LAUNCH_OK("conv_tc_kernel<b2b>");
+    return YL_OK;
+}
+
+bool conv_b2b_supported(const yl_conv_args* a, const yl_conv_args* head) {
+    ConvTcParams p;
+    int grid = 0;
+    size_t smem = 0;
+    ConvTcPlanOpts o;
+    o.head = head;
+    return a && head && plan_conv_tc(a, p, &grid, &smem, &o) == YL_OK;
 }
 
 int launch_conv_tc(const yl_conv_args* a, cudaStream_t stream) {

@@ -67,6 +67,13 @@ struct ConvTcParams {
     float det_conf;              // YL_DET_CLS_FILTER: confidence threshold (strict >)
     uint32_t* det_cand_counts;   //   per-image candidate counters of the NMS workspace
     unsigned long long* det_cand_keys;  // per-image key lists, `det_A` entries each
+    // back-to-back mode (conv_tc_kernel<.., B2B = true>, yl_conv_b2b_det): the conv result is not stored; rounded to bf16 it
+    // is the A operand of a SECOND 1x1 GEMM (weights tmB3, bias3: the head's last conv) whose accumulator feeds the Detect
+    // decode described by det_* (box or class decode)
+    int b2b, k2blocks, co_tile3, nchunks3, acc3_stride, n_bias3, c2_ch;
+    uint32_t b3_bytes;
+    const float* bias3;
+    CUtensorMap tmB3;
     unsigned long long* dbg;     // optional timeline slot (8 x %globaltimer ns, written by CTA 0): yl_debug_timeline
 };
 
@@ -441,6 +448,99 @@ __device__ __forceinline__ void conv_tc_epilogue(const ConvTcParams& p, const Co
     if (leader && g == 0) YL_STAMP(6);
 }
 
+// Epilogue of the back-to-back mode, one group of 4 warps (thread = accumulator row) per accumulator stage:
+//   stage 1  TMEM acc1 -> + bias -> SiLU -> bf16 -> this group's swizzled K-major A2 tiles (one per 64 channels: the layout
+//            of the TMA-store staging tiles IS the UMMA A-operand layout) -> a2_full: the MMA warp runs the second GEMM;
+//   stage 2  TMEM acc2 -> + bias -> Detect box / class decode straight into the prediction (no NHWC store at all).
+template <bool ACT>
+__device__ __forceinline__ void conv_tc_epilogue_b2b(const ConvTcParams& p, const TileRange tr, int g, int q, int lane, int gtid,
+                                                     uint32_t tmem_base, uint64_t* tfull1, uint64_t* tempty1,
+                                                     uint64_t* a2_full, uint64_t* a2_empty, uint64_t* tfull2,
+                                                     uint64_t* tempty2, uint8_t* a2, const float* sbias, const float* sbias3) {
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const uint32_t a2_row = smem_u32(a2) + (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const float bscale = ACT ? 0.5f : 1.0f;
+    float det_dist[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t uses = 0;
+    for (int tile = tr.begin + g * tr.step; tile < tr.end; tile += 2 * tr.step, ++uses) {
+        int nt, wt, ht;
+        int mt = fast_divmod(tile, p.fd_ntiles, &nt);
+        mt = fast_divmod(mt, p.fd_tiles_w, &wt);
+        const int it = fast_divmod(mt, p.fd_tiles_h, &ht);
+        const int w = wt * p.TW + tw, hh = ht * p.TH + th, n = it * p.TN + tn;
+        const bool inside = (tn < p.TN) && (n < p.Nimg) && (hh < p.Ho) && (w < p.Wo);
+        const long long m = inside ? ((long long)n * p.Ho + hh) * p.Wo + w : p.det_M;
+        const uint32_t ph = uses & 1u;
+        mbar_wait(&tfull1[g], ph);
+        tc_fence_after();
+        mbar_wait(&a2_empty[g], ph ^ 1u);     // the second GEMM of this group's previous tile has read the A2 tiles
+        const uint32_t taddr1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.acc_stride);
+        for (int c = 0; c < p.nchunks; ++c) {
+            uint32_t acc[32];
+            tmem_ld32(taddr1 + (uint32_t)(c * 32), acc);
+            tmem_ld_wait();
+            if (c == p.nchunks - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty1[g]);
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + i);
+                v[i + 0] = fmaf(__uint_as_float(acc[i + 0]), bscale, b.x);
+                v[i + 1] = fmaf(__uint_as_float(acc[i + 1]), bscale, b.y);
+                v[i + 2] = fmaf(__uint_as_float(acc[i + 2]), bscale, b.z);
+                v[i + 3] = fmaf(__uint_as_float(acc[i + 3]), bscale, b.w);
+            }
+            if (ACT) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], tanh_approx(v[i]), v[i]);
+            }
+            const uint32_t dst = a2_row + (uint32_t)(c >> 1) * 16384u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t piece = ((uint32_t)((c & 1) * 4 + j)) ^ swz;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (piece << 4)),
+                             "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                             "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                             : "memory");
+            }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + g, kEpiGroupThreads);
+        if (gtid == 0) mbar_arrive(&a2_full[g]);
+
+        mbar_wait(&tfull2[g], ph);
+        tc_fence_after();
+        const uint32_t taddr2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.acc_stride + g * p.acc3_stride);
+        for (int c = 0; c < p.nchunks3; ++c) {
+            uint32_t acc[32];
+            tmem_ld32(taddr2 + (uint32_t)(c * 32), acc);
+            tmem_ld_wait();
+            if (c == p.nchunks3 - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty2[g]);
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias3 + c * 32 + i);
+                v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
+                v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+                v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
+                v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+            }
+            det_decode_chunk<32>(p, v, c, m, det_dist, p.det_mode);
+        }
+    }
+}
+
 // host side (conv_tc.cu)
 bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw);
@@ -453,6 +553,7 @@ struct ConvTcPlanOpts {
                             // (no halo patch / resident weights), N tiles <= 128 columns (two CTAs per SM), no batch-size
                             // dependent dispatch
     int chain_cluster = 4;  // CTAs per image (cluster size)
+    const yl_conv_args* head = nullptr;   // back-to-back mode: the head's last 1x1 conv (Detect box / class decode, no store)
 };
 int plan_conv_tc(const yl_conv_args* a, ConvTcParams& p, int* grid_out, size_t* smem_out, const ConvTcPlanOpts* opts = nullptr);
 

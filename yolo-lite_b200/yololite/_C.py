@@ -125,6 +125,8 @@ _PROTOTYPES = {
     "yl_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "yl_conv_bn_act": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "yl_conv_tc_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "yl_conv_b2b_det_supported": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvArgs)]),
+    "yl_conv_b2b_det": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvArgs), C.c_void_p]),
     "yl_conv_tc_info": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvTcPlan)]),
     "yl_conv_chain_desc_bytes": (C.c_size_t, [C.c_int]),
     "yl_conv_chain_supported": (C.c_int, [C.POINTER(ConvArgs)]),

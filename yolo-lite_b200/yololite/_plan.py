@@ -84,6 +84,10 @@ class Builder:
         # DWConv 3x3 + Conv 1x1 pairs (Detect class branch) as one launch (csrc/dwpw_tc.cu)
         self.dwpw_enabled = os.environ.get("YL_DWPW", "1") != "0"
         self.dwpw_det_enabled = os.environ.get("YL_DWPW_DET", "1") != "0"
+        # tail of the Detect box branch (Conv 3x3 + final 1x1 + box decode) as one back-to-back launch: opt-in.  Bit-identical
+        # and 12 us less kernel time per step, but the step got 1.3 % SLOWER (40.5 k vs 41.0 k images/s): the longer kernels
+        # overlap worse with the class-branch kernels on the other graph lanes (profiles/r02_SUMMARY.md)
+        self.conv_det_enabled = os.environ.get("YL_CONV_DET", "0") == "1"
 
     # ------------------------------------------------------------------ memory
     def alloc(self, n, h, w, c, dtype=torch.bfloat16) -> View:
@@ -247,6 +251,29 @@ class Builder:
                    flops=2 * px * (9 * x.c + x.c * ppw.co), desc=f"[dw3x3 {x.c}, {x.c}->{ppw.co} k1] {x.h}x{x.w}",
                    reads=(x,), writes=(y,))
         return y
+
+    def conv_det(self, x: View, pc: PackedConv, act: bool, plast: PackedConv, det) -> bool:
+        """Tail of a Detect box branch on the engine path: Conv k x k (+BN+act) + the final 1x1 conv with its Detect decode
+        (no NHWC store) as ONE launch (yl_conv_b2b_det: back-to-back tcgen05 GEMMs, the tensor between them stays in shared
+        memory).  False when the kernel does not take the shape."""
+        x = self.mat(x)
+        if not (self.conv_det_enabled and not pc.depthwise and not plast.depthwise and plast.k == 1 and plast.ci == pc.co):
+            return False
+        ho, wo = x.h, x.w                         # stride 1, 'same' padding
+        mid = _ops.NoOutput(x.n, ho, wo, pc.co, torch.bfloat16)
+        a1 = _ops.conv_args(x, mid, pc, 1, act, None, False, _C.IMPL_TCGEN05, None, None)
+        a2 = _ops.conv_args(mid, _ops.NoOutput(x.n, ho, wo, plast.co, torch.float32), plast, 1, False, None, False,
+                            _C.IMPL_TCGEN05, None, det)
+        if not self.lib.yl_conv_b2b_det_supported(C.byref(a1), C.byref(a2)):
+            return False
+        px = x.n * ho * wo
+        rows = 4 if det.mode == _C.DET_BOX else det.nc
+        self._push(self.lib.yl_conv_b2b_det, C.byref(a1), C.byref(a2), keep=(a1, a2, pc, plast, det), kind="conv_tc",
+                   bytes_=px * x.c * 2 + px * rows * 4 + (pc.k * pc.k * x.c * pc.co + pc.co * plast.co) * 2,
+                   flops=2 * px * (pc.k * pc.k * x.c * pc.co + pc.co * plast.co),
+                   desc=f"[{x.c}->{pc.co} k{pc.k}s1, {pc.co}->{plast.co} k1 +decode] {x.h}x{x.w}", reads=(x,),
+                   writes=((det.pred, 2 * det.anchor0 + (det.mode == _C.DET_CLS), 2 * det.anchor0 + (det.mode == _C.DET_CLS) + 1),))
+        return True
 
     def dwpw_det(self, x: View, pdw: PackedConv, act_dw: bool, ppw: PackedConv, act_pw: bool, plast: PackedConv, det) -> bool:
         """Last stage of a Detect class branch on the engine path: DWConv 3x3 + Conv 1x1 + the final 1x1 conv with its

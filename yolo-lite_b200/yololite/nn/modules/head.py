@@ -124,6 +124,8 @@ class Detect(YLModule):
                     # one back-to-back launch when the kernel takes the shape
                     if mode == _C.DET_CLS and not want_raw and self._emit_cls_tail(g, branch, x, det):
                         continue
+                    if mode == _C.DET_BOX and not want_raw and self._emit_box_tail(g, branch, x, det):
+                        continue
                     t = self._emit_branch(g, branch[:-1], x)
                     g.conv(t, packed(last, None, last), 1, act=False, out=raw.slice(lo, cnt) if want_raw else None,
                            out_dtype=torch.float32, det=det, store=want_raw)
@@ -148,6 +150,26 @@ class Detect(YLModule):
                            act_flag(pw.act))
             x = y if y is not None else emit_any(g, sub, x)
         return x
+
+    @classmethod
+    def _emit_box_tail(cls, g, branch, x, det) -> bool:
+        """[..., Conv k3, Conv2d 1x1 + box decode] with the last two as ONE launch (yl_conv_b2b_det).  Emits the earlier
+        convs and returns True, or emits nothing and returns False."""
+        from ._emit import act_flag, packed
+
+        if len(branch) < 2 or not isinstance(branch[-1], nn.Conv2d) or type(branch[-2]) is not Conv:
+            return False
+        cv, last = branch[-2], branch[-1]
+        if not (cv.conv.stride == (1, 1) and cv.conv.groups == 1 and last.kernel_size == (1, 1) and last.stride == (1, 1)
+                and last.groups == 1 and g.conv_det_enabled):
+            return False
+        t = cls._emit_branch(g, branch[:-2], x)
+        if g.conv_det(g.mat(t), packed(cv.conv, cv.bn, cv), act_flag(cv.act), packed(last, None, last), det):
+            return True
+        # the back-to-back kernel does not take the shape: finish the branch the plain way
+        t = cls._emit_branch(g, branch[-2:-1], t)
+        g.conv(t, packed(last, None, last), 1, act=False, out=None, out_dtype=torch.float32, det=det, store=False)
+        return True
 
     @classmethod
     def _emit_cls_tail(cls, g, branch, x, det) -> bool:
