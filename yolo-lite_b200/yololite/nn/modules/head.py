@@ -112,7 +112,8 @@ class Detect(YLModule):
                                                           (self.cv3[i], _C.DET_CLS, nbox, self.nc))):
                 # every (level, branch) chain depends only on its pyramid feature: side lanes let the graph run
                 # them next to the rest of the neck (the last level's box branch stays on the main lane)
-                lane = 0 if (i == self.nl - 1 and j == 0) or not self.parallel_branches else 1 + 2 * i + j
+                lanes_on = self.parallel_branches and os.environ.get("YL_DET_LANES", "1") != "0"
+                lane = 0 if (i == self.nl - 1 and j == 0) or not lanes_on else 1 + 2 * i + j
                 with g.lane(lane):
                     last = branch[-1]
                     if filt and mode == _C.DET_CLS:
